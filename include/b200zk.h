@@ -1,0 +1,114 @@
+/* b200zk — C ABI of the sm_100a PLONK hot path (BN254 G1 MSM + fr NTT) for noir_backend_using_gnark.
+ *
+ * This is the inner drop-in boundary (SURVEY.md §8b "B-inner"): the functions a cgo shim inside
+ * gnark_backend_ffi binds in place of gnark-crypto's CPU arithmetic.  The outer boundary — the four cgo exports
+ * PlonkProveWithPK / PlonkVerifyWithVK / PlonkPreprocess / PlonkVerifyWithMeta at
+ * /root/reference/gnark_backend_ffi/main.go:24,44,58,39 — stays byte-for-byte as the reference defines it.
+ *
+ * Conventions (identical to gnark-crypto v0.9.1 in-memory layouts, so Go slices can be passed without copies):
+ *   fr.Element / fp.Element : 32 bytes = 4 x uint64 little-endian limbs, Montgomery form (R = 2^256), fully reduced
+ *   G1Affine                : 64 bytes = X || Y, point at infinity = 64 zero bytes
+ *   decimation              : 0 = DIF (natural in -> bit-reversed out), 1 = DIT (bit-reversed in -> natural out)
+ *
+ * Every function returns 0 on success or a negative b200zk_error; nothing aborts or throws across the boundary
+ * (the Go shim turns a non-zero code into log.Fatal to match /root/reference/gnark_backend_ffi/backend/plonk/plonk.go:69).
+ * A context is bound to ONE device and may be used from one thread at a time; every entry point re-selects the
+ * context's device, so it can be called from any OS thread (Go moves goroutines between threads).
+ * There is no CPU fallback: without a CUDA device b200zk_init fails with B200ZK_ERR_NO_DEVICE.
+ */
+#ifndef B200ZK_H
+#define B200ZK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200zk_ctx b200zk_ctx;
+typedef struct b200zk_bases b200zk_bases;
+
+typedef enum b200zk_error {
+  B200ZK_OK = 0,
+  B200ZK_ERR_NO_DEVICE = -1,   /* no CUDA device / device index out of range */
+  B200ZK_ERR_CUDA = -2,        /* a CUDA runtime call failed; see b200zk_last_cuda_error */
+  B200ZK_ERR_BAD_ARG = -3,     /* null pointer, log2n > 28, n > bases, ... */
+  B200ZK_ERR_OOM = -4,         /* device allocation failed */
+  B200ZK_ERR_UNSUPPORTED = -5
+} b200zk_error;
+
+enum { B200ZK_DIF = 0, B200ZK_DIT = 1 };
+enum { B200ZK_MAX_LOG2N = 28 }; /* 2-adicity of BN254 fr */
+
+/* ---- lifecycle ------------------------------------------------------------------------------------------ */
+int b200zk_device_count(void);
+int b200zk_init(int device, b200zk_ctx** out);
+void b200zk_destroy(b200zk_ctx* ctx);
+const char* b200zk_strerror(int code);
+const char* b200zk_last_cuda_error(const b200zk_ctx* ctx);
+/* CUDA stream (cudaStream_t) all work of this context is enqueued on; *_dev calls are asynchronous on it. */
+void* b200zk_stream(b200zk_ctx* ctx);
+int b200zk_sync(b200zk_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t b200zk_launch_count(const b200zk_ctx* ctx);
+
+/* ---- fr NTT ---------------------------------------------------------------------------------------------
+ * b200zk_ntt == (*fft.Domain).FFT(a, decimation, coset) when inverse == 0 and
+ *               (*fft.Domain).FFTInverse(a, decimation, coset) when inverse != 0,
+ * for domain = fft.NewDomain(1 << log2n) of gnark-crypto v0.9.1 ecc/bn254/fr/fft (Generator = g^(2^(28-log2n)),
+ * FrMultiplicativeGen = 5), reached in the reference through plonk.Prove / plonk.Setup
+ * (/root/reference/gnark_backend_ffi/backend/plonk/plonk.go:67, :21).  In place; `a` holds 2^log2n fr.Element.
+ * b200zk_ntt takes a HOST pointer (copies in and out); b200zk_ntt_dev takes a DEVICE pointer on the context's
+ * device and only enqueues work on the context stream. */
+int b200zk_ntt(b200zk_ctx* ctx, void* a_host, unsigned log2n, int inverse, int decimation, int coset);
+int b200zk_ntt_dev(b200zk_ctx* ctx, void* a_dev, unsigned log2n, int inverse, int decimation, int coset);
+/* fft.BitReverse(a): in-place index bit-reversal permutation. */
+int b200zk_bit_reverse(b200zk_ctx* ctx, void* a_host, unsigned log2n);
+int b200zk_bit_reverse_dev(b200zk_ctx* ctx, void* a_dev, unsigned log2n);
+
+/* ---- G1 MSM ---------------------------------------------------------------------------------------------
+ * Bases are the KZG SRS G1 powers kzg.SRS.G1 (loaded at /root/reference/gnark_backend_ffi/backend/common.go:86-105,
+ * attached by InitKZG at backend/plonk/plonk.go:62); they are static across calls, so they are uploaded once.
+ * b200zk_msm_g1 == (*G1Affine).MultiExp(points[:n], scalars[:n], cfg) of gnark-crypto v0.9.1 ecc/bn254/multiexp.go,
+ * as called by kzg.Commit: scalars are Montgomery-form fr.Element; result is the canonical affine point. */
+int b200zk_bases_upload(b200zk_ctx* ctx, const void* g1_affine_host, size_t n, b200zk_bases** out);
+/* wrap n points already resident on the context's device (no copy; caller keeps them alive) */
+int b200zk_bases_wrap_dev(b200zk_ctx* ctx, const void* g1_affine_dev, size_t n, b200zk_bases** out);
+/* kzg.NewSRS(size, alpha).G1[first .. first+n) computed on the device: bases[i] = alpha^(first+i) * G
+ * (/root/reference/gnark_backend_ffi/backend/common.go:137, main.go:176).  alpha: one Montgomery-form fr.Element;
+ * first > 0 produces the point-range shard of one GPU. */
+int b200zk_srs_generate(b200zk_ctx* ctx, const void* alpha_host, size_t first, size_t n, b200zk_bases** out);
+/* copy bases[first .. first+n) back to the host (64 B each), e.g. to serialise a generated SRS */
+int b200zk_bases_download(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first, size_t n, void* out_host);
+void b200zk_bases_free(b200zk_ctx* ctx, b200zk_bases* bases);
+size_t b200zk_bases_len(const b200zk_bases* bases);
+
+int b200zk_msm_g1(b200zk_ctx* ctx, const b200zk_bases* bases, const void* scalars_host, size_t n,
+                  void* out_affine_host /* 64 B */);
+/* Device-resident variant.  first_base = index of the base paired with scalars[0] (point-range shard).
+ * out_kind 0: canonical affine (64 B); 1: extended-Jacobian partial X,Y,ZZ,ZZZ (128 B) to be combined across
+ * GPUs with b200zk_g1_sum_dev.  Asynchronous on the context stream. */
+int b200zk_msm_g1_dev(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const void* scalars_dev,
+                      size_t n, void* out_dev, int out_kind);
+/* out_affine_dev (64 B) = canonical affine of the sum of `count` extended-Jacobian partials (128 B each). */
+int b200zk_g1_sum_dev(b200zk_ctx* ctx, const void* partials_dev, size_t count, void* out_affine_dev);
+/* force the Pippenger window size (0 = choose from n); for tests and tuning */
+int b200zk_msm_set_window(b200zk_ctx* ctx, int c);
+
+
+/* ---- measurement ----------------------------------------------------------------------------------------
+ * Integer-pipe microbenchmarks used as roofline denominators (synchronous).  which = 0: IMAD.WIDE.U32 multiply-
+ * accumulates per second; 1: fp Montgomery multiplications per second; 2: fr Montgomery multiplications per second. */
+int b200zk_microbench(b200zk_ctx* ctx, int which, double* out_ops_per_s);
+/* Per-phase device timing with CUDA events on the context stream.  Phases: 0 msm digits+histogram, 1 msm scan,
+ * 2 msm scatter, 3 msm bucket accumulation, 4 msm long-run path, 5 msm bucket reduction, 6 msm final, 7 ntt pass.
+ * b200zk_profile_read synchronises, returns the summed milliseconds and launch-group counts since the last read
+ * (arrays of at least 8 entries) and clears the records. */
+int b200zk_profile_enable(b200zk_ctx* ctx, int on);
+int b200zk_profile_read(b200zk_ctx* ctx, double* ms_per_phase, uint64_t* count_per_phase, int nphases);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ZK_H */

@@ -1,0 +1,88 @@
+"""ctypes binding of libb200zk.so (include/b200zk.h).  Fails loudly when the library is missing: there is no
+CPU fallback anywhere in this package."""
+from __future__ import annotations
+
+import ctypes as C
+import re
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "lib" / "libb200zk.so"
+HEADER = PKG.parent / "include" / "b200zk.h"
+
+DIF, DIT = 0, 1
+MAX_LOG2N = 28
+
+
+class B200zkError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("b200zk error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def header_symbols() -> list[str]:
+    """Every function name declared in include/b200zk.h."""
+    text = HEADER.read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200zk_[a-z0-9_]+)\s*\(", text)))
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise ImportError(
+            "%s is missing: build it with `python -m noir_backend_using_gnark_b200.build` "
+            "(this package has no CPU fallback)" % LIB_PATH
+        )
+    lib = C.CDLL(str(LIB_PATH))
+    vp, sz, u, i = C.c_void_p, C.c_size_t, C.c_uint, C.c_int
+    sig = {
+        "b200zk_device_count": (i, []),
+        "b200zk_init": (i, [i, C.POINTER(vp)]),
+        "b200zk_destroy": (None, [vp]),
+        "b200zk_strerror": (C.c_char_p, [i]),
+        "b200zk_last_cuda_error": (C.c_char_p, [vp]),
+        "b200zk_stream": (vp, [vp]),
+        "b200zk_sync": (i, [vp]),
+        "b200zk_launch_count": (C.c_uint64, [vp]),
+        "b200zk_ntt": (i, [vp, vp, u, i, i, i]),
+        "b200zk_ntt_dev": (i, [vp, vp, u, i, i, i]),
+        "b200zk_bit_reverse": (i, [vp, vp, u]),
+        "b200zk_bit_reverse_dev": (i, [vp, vp, u]),
+        "b200zk_bases_upload": (i, [vp, vp, sz, C.POINTER(vp)]),
+        "b200zk_bases_wrap_dev": (i, [vp, vp, sz, C.POINTER(vp)]),
+        "b200zk_srs_generate": (i, [vp, vp, sz, sz, C.POINTER(vp)]),
+        "b200zk_bases_download": (i, [vp, vp, sz, sz, vp]),
+        "b200zk_bases_free": (None, [vp, vp]),
+        "b200zk_bases_len": (sz, [vp]),
+        "b200zk_msm_g1": (i, [vp, vp, vp, sz, vp]),
+        "b200zk_msm_g1_dev": (i, [vp, vp, sz, vp, sz, vp, i]),
+        "b200zk_g1_sum_dev": (i, [vp, vp, sz, vp]),
+        "b200zk_msm_set_window": (i, [vp, i]),
+        "b200zk_microbench": (i, [vp, i, C.POINTER(C.c_double)]),
+        "b200zk_profile_enable": (i, [vp, i]),
+        "b200zk_profile_read": (i, [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), i]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    lib._signatures = sig
+    _lib = lib
+    return lib
+
+
+def check(ctx, rc: int) -> None:
+    if rc != 0:
+        lib = load()
+        msg = lib.b200zk_strerror(rc).decode()
+        if ctx:
+            detail = lib.b200zk_last_cuda_error(ctx).decode()
+            if detail:
+                msg += " (" + detail + ")"
+        raise B200zkError(rc, msg)

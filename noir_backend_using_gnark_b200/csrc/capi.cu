@@ -1,0 +1,296 @@
+// C ABI of libb200zk (declared in include/b200zk.h).  No exceptions, no aborts: every failure is an error code.
+#include <new>
+#include "common.cuh"
+
+using namespace b200zk;
+
+namespace {
+
+int enter(b200zk_ctx* ctx) {
+  if (!ctx) return B200ZK_ERR_BAD_ARG;
+  cudaError_t e = cudaSetDevice(ctx->device);
+  if (e != cudaSuccess) return set_cuda_error(ctx, e, "cudaSetDevice");
+  return B200ZK_OK;
+}
+
+void free_buf(DeviceBuf& b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200zk_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int b200zk_init(int device, b200zk_ctx** out) {
+  if (!out) return B200ZK_ERR_BAD_ARG;
+  *out = nullptr;
+  int n = b200zk_device_count();
+  if (n <= 0 || device < 0 || device >= n) return B200ZK_ERR_NO_DEVICE;
+  if (cudaSetDevice(device) != cudaSuccess) {
+    cudaGetLastError();
+    return B200ZK_ERR_NO_DEVICE;
+  }
+  b200zk_ctx* ctx = new (std::nothrow) b200zk_ctx();
+  if (!ctx) return B200ZK_ERR_OOM;
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    cudaGetLastError();
+    delete ctx;
+    return B200ZK_ERR_CUDA;
+  }
+  *out = ctx;
+  return B200ZK_OK;
+}
+
+void b200zk_destroy(b200zk_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  ntt_free_domains(ctx);
+  free_buf(ctx->stage);
+  free_buf(ctx->msm_digits);
+  free_buf(ctx->msm_sorted);
+  free_buf(ctx->msm_counts);
+  free_buf(ctx->msm_starts);
+  free_buf(ctx->msm_cursor);
+  free_buf(ctx->msm_buckets);
+  free_buf(ctx->msm_tmp);
+  free_buf(ctx->msm_small);
+  free_buf(ctx->msm_scan_tmp);
+  free_buf(ctx->msm_big);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* b200zk_strerror(int code) {
+  switch (code) {
+    case B200ZK_OK: return "ok";
+    case B200ZK_ERR_NO_DEVICE: return "no usable CUDA device (libb200zk has no CPU fallback)";
+    case B200ZK_ERR_CUDA: return "CUDA runtime error";
+    case B200ZK_ERR_BAD_ARG: return "bad argument";
+    case B200ZK_ERR_OOM: return "out of device memory";
+    case B200ZK_ERR_UNSUPPORTED: return "unsupported size";
+    default: return "unknown error";
+  }
+}
+
+const char* b200zk_last_cuda_error(const b200zk_ctx* ctx) { return ctx ? ctx->cuda_err : ""; }
+void* b200zk_stream(b200zk_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+uint64_t b200zk_launch_count(const b200zk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int b200zk_sync(b200zk_ctx* ctx) {
+  B200ZK_TRY(enter(ctx));
+  B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200ZK_OK;
+}
+
+// ---- NTT ---------------------------------------------------------------------------------------------------
+int b200zk_ntt_dev(b200zk_ctx* ctx, void* a_dev, unsigned log2n, int inverse, int decimation, int coset) {
+  B200ZK_TRY(enter(ctx));
+  if (!a_dev || log2n > B200ZK_MAX_LOG2N || (decimation != B200ZK_DIF && decimation != B200ZK_DIT))
+    return B200ZK_ERR_BAD_ARG;
+  return ntt_run(ctx, a_dev, log2n, inverse != 0, decimation, coset != 0);
+}
+
+int b200zk_ntt(b200zk_ctx* ctx, void* a_host, unsigned log2n, int inverse, int decimation, int coset) {
+  B200ZK_TRY(enter(ctx));
+  if (!a_host || log2n > B200ZK_MAX_LOG2N || (decimation != B200ZK_DIF && decimation != B200ZK_DIT))
+    return B200ZK_ERR_BAD_ARG;
+  const size_t bytes = ((size_t)1 << log2n) * 32;
+  B200ZK_TRY(ensure(ctx, ctx->stage, bytes));
+  B200ZK_CUDA(ctx, cudaMemcpyAsync(ctx->stage.p, a_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  B200ZK_TRY(ntt_run(ctx, ctx->stage.p, log2n, inverse != 0, decimation, coset != 0));
+  B200ZK_CUDA(ctx, cudaMemcpyAsync(a_host, ctx->stage.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200ZK_OK;
+}
+
+int b200zk_bit_reverse_dev(b200zk_ctx* ctx, void* a_dev, unsigned log2n) {
+  B200ZK_TRY(enter(ctx));
+  if (!a_dev || log2n > B200ZK_MAX_LOG2N) return B200ZK_ERR_BAD_ARG;
+  return bit_reverse_run(ctx, a_dev, log2n);
+}
+
+int b200zk_bit_reverse(b200zk_ctx* ctx, void* a_host, unsigned log2n) {
+  B200ZK_TRY(enter(ctx));
+  if (!a_host || log2n > B200ZK_MAX_LOG2N) return B200ZK_ERR_BAD_ARG;
+  const size_t bytes = ((size_t)1 << log2n) * 32;
+  B200ZK_TRY(ensure(ctx, ctx->stage, bytes));
+  B200ZK_CUDA(ctx, cudaMemcpyAsync(ctx->stage.p, a_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  B200ZK_TRY(bit_reverse_run(ctx, ctx->stage.p, log2n));
+  B200ZK_CUDA(ctx, cudaMemcpyAsync(a_host, ctx->stage.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200ZK_OK;
+}
+
+// ---- MSM ---------------------------------------------------------------------------------------------------
+int b200zk_bases_upload(b200zk_ctx* ctx, const void* g1_affine_host, size_t n, b200zk_bases** out) {
+  B200ZK_TRY(enter(ctx));
+  if (!out || (n && !g1_affine_host)) return B200ZK_ERR_BAD_ARG;
+  *out = nullptr;
+  b200zk_bases* b = new (std::nothrow) b200zk_bases();
+  if (!b) return B200ZK_ERR_OOM;
+  void* dev = nullptr;
+  cudaError_t e = cudaMalloc(&dev, n ? n * 64 : 64);
+  if (e != cudaSuccess) {
+    delete b;
+    return set_cuda_error(ctx, e, "cudaMalloc(bases)");
+  }
+  if (n) {
+    e = cudaMemcpyAsync(dev, g1_affine_host, n * 64, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      cudaFree(dev);
+      delete b;
+      return set_cuda_error(ctx, e, "cudaMemcpy(bases)");
+    }
+  }
+  b->dev = dev;
+  b->n = n;
+  b->owned = true;
+  *out = b;
+  return B200ZK_OK;
+}
+
+int b200zk_bases_wrap_dev(b200zk_ctx* ctx, const void* g1_affine_dev, size_t n, b200zk_bases** out) {
+  B200ZK_TRY(enter(ctx));
+  if (!out || (n && !g1_affine_dev)) return B200ZK_ERR_BAD_ARG;
+  b200zk_bases* b = new (std::nothrow) b200zk_bases();
+  if (!b) return B200ZK_ERR_OOM;
+  b->dev = g1_affine_dev;
+  b->n = n;
+  b->owned = false;
+  *out = b;
+  return B200ZK_OK;
+}
+
+void b200zk_bases_free(b200zk_ctx* ctx, b200zk_bases* bases) {
+  if (!bases) return;
+  if (bases->owned && bases->dev) {
+    if (ctx) {
+      cudaSetDevice(ctx->device);
+      cudaStreamSynchronize(ctx->stream);
+    }
+    cudaFree(const_cast<void*>(bases->dev));
+  }
+  delete bases;
+}
+
+size_t b200zk_bases_len(const b200zk_bases* bases) { return bases ? bases->n : 0; }
+
+int b200zk_msm_g1_dev(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const void* scalars_dev,
+                      size_t n, void* out_dev, int out_kind) {
+  B200ZK_TRY(enter(ctx));
+  if (out_kind != 0 && out_kind != 1) return B200ZK_ERR_BAD_ARG;
+  return msm_run(ctx, bases, first_base, scalars_dev, n, out_dev, out_kind);
+}
+
+int b200zk_msm_g1(b200zk_ctx* ctx, const b200zk_bases* bases, const void* scalars_host, size_t n,
+                  void* out_affine_host) {
+  B200ZK_TRY(enter(ctx));
+  if (!bases || !out_affine_host || (n && !scalars_host) || n > bases->n) return B200ZK_ERR_BAD_ARG;
+  const size_t bytes = n * 32 + 64;
+  B200ZK_TRY(ensure(ctx, ctx->stage, bytes));
+  char* stage = (char*)ctx->stage.p;
+  if (n) B200ZK_CUDA(ctx, cudaMemcpyAsync(stage + 64, scalars_host, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  B200ZK_TRY(msm_run(ctx, bases, 0, stage + 64, n, stage, 0));
+  B200ZK_CUDA(ctx, cudaMemcpyAsync(out_affine_host, stage, 64, cudaMemcpyDeviceToHost, ctx->stream));
+  B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200ZK_OK;
+}
+
+int b200zk_g1_sum_dev(b200zk_ctx* ctx, const void* partials_dev, size_t count, void* out_affine_dev) {
+  B200ZK_TRY(enter(ctx));
+  return g1_sum_run(ctx, partials_dev, count, out_affine_dev);
+}
+
+int b200zk_srs_generate(b200zk_ctx* ctx, const void* alpha_host, size_t first, size_t n, b200zk_bases** out) {
+  B200ZK_TRY(enter(ctx));
+  if (!alpha_host || !out) return B200ZK_ERR_BAD_ARG;
+  *out = nullptr;
+  b200zk_bases* b = new (std::nothrow) b200zk_bases();
+  if (!b) return B200ZK_ERR_OOM;
+  void* dev = nullptr;
+  cudaError_t e = cudaMalloc(&dev, (n ? n : 1) * 64 + 32);
+  if (e != cudaSuccess) {
+    delete b;
+    return set_cuda_error(ctx, e, "cudaMalloc(srs)");
+  }
+  char* alpha_dev = (char*)dev + (n ? n : 1) * 64;
+  e = cudaMemcpyAsync(alpha_dev, alpha_host, 32, cudaMemcpyHostToDevice, ctx->stream);
+  int rc = e == cudaSuccess ? srs_generate_run(ctx, alpha_dev, first, n, dev) : set_cuda_error(ctx, e, "cudaMemcpy(alpha)");
+  if (rc != B200ZK_OK) {
+    cudaFree(dev);
+    delete b;
+    return rc;
+  }
+  b->dev = dev;
+  b->n = n;
+  b->owned = true;
+  *out = b;
+  return B200ZK_OK;
+}
+
+int b200zk_bases_download(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first, size_t n, void* out_host) {
+  B200ZK_TRY(enter(ctx));
+  if (!bases || !out_host || first > bases->n || n > bases->n - first) return B200ZK_ERR_BAD_ARG;
+  B200ZK_CUDA(ctx, cudaMemcpyAsync(out_host, (const char*)bases->dev + first * 64, n * 64, cudaMemcpyDeviceToHost,
+                                   ctx->stream));
+  B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200ZK_OK;
+}
+
+int b200zk_profile_enable(b200zk_ctx* ctx, int on) {
+  B200ZK_TRY(enter(ctx));
+  ctx->profiling = on != 0;
+  return B200ZK_OK;
+}
+
+int b200zk_profile_read(b200zk_ctx* ctx, double* ms_per_phase, uint64_t* count_per_phase, int nphases) {
+  B200ZK_TRY(enter(ctx));
+  if (!ms_per_phase || !count_per_phase || nphases < PH_COUNT) return B200ZK_ERR_BAD_ARG;
+  B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < nphases; i++) {
+    ms_per_phase[i] = 0;
+    count_per_phase[i] = 0;
+  }
+  for (auto& r : ctx->records) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+      ms_per_phase[r.phase] += ms;
+      count_per_phase[r.phase]++;
+    } else {
+      cudaGetLastError();
+    }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  ctx->records.clear();
+  return B200ZK_OK;
+}
+
+int b200zk_microbench(b200zk_ctx* ctx, int which, double* out_ops_per_s) {
+  B200ZK_TRY(enter(ctx));
+  return microbench_run(ctx, which, out_ops_per_s);
+}
+
+int b200zk_msm_set_window(b200zk_ctx* ctx, int c) {
+  if (!ctx || (c != 0 && (c < 6 || c > 16))) return B200ZK_ERR_BAD_ARG;
+  ctx->forced_window = c;
+  return B200ZK_OK;
+}
+
+}  // extern "C"

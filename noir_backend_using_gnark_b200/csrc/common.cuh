@@ -1,0 +1,149 @@
+// Context, workspace and error plumbing shared by the NTT / MSM translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#include "../../include/b200zk.h"
+
+namespace b200zk {
+
+struct NttDomain {
+  bool ready = false;
+  unsigned log2n = 0;
+  // tw[i] = w^i (forward) / w^-i (inverse) for i < max(1, N/2): full tables, no extra multiplications per butterfly
+  void* tw_fwd = nullptr;
+  void* tw_inv = nullptr;
+  // two-level coset tables: 5^e = lo[e & (LO-1)] * hi[e >> LO_BITS];  the inverse lo table carries the 1/n factor
+  void* coset_lo = nullptr;
+  void* coset_hi = nullptr;
+  void* coset_inv_lo = nullptr;
+  void* coset_inv_hi = nullptr;
+  void* scalars = nullptr;  // [0] = 1/n (Montgomery)
+};
+
+// phases timed with CUDA events when profiling is enabled (b200zk_profile_*)
+enum Phase {
+  PH_MSM_DIGITS = 0, PH_MSM_SCAN = 1, PH_MSM_SCATTER = 2, PH_MSM_ACCUMULATE = 3, PH_MSM_BIG = 4, PH_MSM_REDUCE = 5,
+  PH_MSM_FINAL = 6, PH_NTT_PASS = 7, PH_COUNT = 8
+};
+struct PhaseRecord {
+  int phase;
+  cudaEvent_t e0, e1;
+};
+
+struct DeviceBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+}  // namespace b200zk
+
+struct b200zk_bases {
+  const void* dev = nullptr;  // n x 64 B affine points
+  size_t n = 0;
+  bool owned = false;
+};
+
+struct b200zk_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  uint64_t launches = 0;
+  char cuda_err[256] = {0};
+  int forced_window = 0;
+  bool profiling = false;
+  std::vector<b200zk::PhaseRecord> records;
+  b200zk::NttDomain domains[B200ZK_MAX_LOG2N + 1];
+  // staging buffer for host-pointer entry points
+  b200zk::DeviceBuf stage;
+  // MSM workspace (grown on demand, reused across calls)
+  b200zk::DeviceBuf msm_digits, msm_sorted, msm_counts, msm_starts, msm_cursor, msm_buckets, msm_tmp, msm_small,
+      msm_scan_tmp, msm_big;
+};
+
+namespace b200zk {
+
+inline int set_cuda_error(b200zk_ctx* ctx, cudaError_t e, const char* where) {
+  if (ctx) snprintf(ctx->cuda_err, sizeof(ctx->cuda_err), "%s: %s", where, cudaGetErrorString(e));
+  cudaGetLastError();
+  return e == cudaErrorMemoryAllocation ? B200ZK_ERR_OOM : B200ZK_ERR_CUDA;
+}
+
+#define B200ZK_CUDA(ctx, call)                                                \
+  do {                                                                        \
+    cudaError_t e__ = (call);                                                 \
+    if (e__ != cudaSuccess) return b200zk::set_cuda_error(ctx, e__, #call);   \
+  } while (0)
+
+#define B200ZK_LAUNCH_CHECK(ctx, name)                                        \
+  do {                                                                        \
+    (ctx)->launches++;                                                        \
+    cudaError_t e__ = cudaGetLastError();                                     \
+    if (e__ != cudaSuccess) return b200zk::set_cuda_error(ctx, e__, name);    \
+  } while (0)
+
+#define B200ZK_TRY(expr)                \
+  do {                                  \
+    int rc__ = (expr);                  \
+    if (rc__ != B200ZK_OK) return rc__; \
+  } while (0)
+
+inline int ensure(b200zk_ctx* ctx, DeviceBuf& b, size_t bytes) {
+  if (b.cap >= bytes) return B200ZK_OK;
+  if (b.p) {
+    // the buffer may still be in use by work enqueued earlier on the stream
+    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    B200ZK_CUDA(ctx, cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+  }
+  size_t want = bytes + (bytes >> 3);
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    want = bytes;
+    e = cudaMalloc(&b.p, want);
+  }
+  if (e != cudaSuccess) {
+    b.p = nullptr;
+    return set_cuda_error(ctx, e, "cudaMalloc(workspace)");
+  }
+  b.cap = want;
+  return B200ZK_OK;
+}
+
+// RAII phase timer: records an event pair around a group of launches when ctx->profiling is on
+struct PhaseTimer {
+  b200zk_ctx* ctx;
+  PhaseRecord rec;
+  bool on;
+  PhaseTimer(b200zk_ctx* c, int phase) : ctx(c), on(c->profiling) {
+    if (!on) return;
+    rec.phase = phase;
+    if (cudaEventCreate(&rec.e0) != cudaSuccess || cudaEventCreate(&rec.e1) != cudaSuccess) {
+      on = false;
+      cudaGetLastError();
+      return;
+    }
+    cudaEventRecord(rec.e0, ctx->stream);
+  }
+  ~PhaseTimer() {
+    if (!on) return;
+    cudaEventRecord(rec.e1, ctx->stream);
+    ctx->records.push_back(rec);
+  }
+};
+
+// entry points implemented in ntt.cu / msm.cu
+int ntt_run(b200zk_ctx* ctx, void* a_dev, unsigned log2n, int inverse, int decimation, int coset);
+int bit_reverse_run(b200zk_ctx* ctx, void* a_dev, unsigned log2n);
+void ntt_free_domains(b200zk_ctx* ctx);
+int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const void* scalars_dev, size_t n,
+            void* out_dev, int out_kind);
+int g1_sum_run(b200zk_ctx* ctx, const void* partials_dev, size_t count, void* out_affine_dev);
+int microbench_run(b200zk_ctx* ctx, int which, double* out_ops_per_s);
+int srs_generate_run(b200zk_ctx* ctx, const void* alpha_dev, size_t first, size_t n, void* out_dev);
+
+}  // namespace b200zk

@@ -1,0 +1,383 @@
+// BN254 fp / fr Montgomery arithmetic for sm_100a.
+//
+// Replaces (device side) gnark-crypto v0.9.1 ecc/bn254/{fp,fr}/element.go — the arithmetic reached from
+// /root/reference/gnark_backend_ffi/backend/plonk/plonk.go:67 (plonk.Prove) through kzg.Commit / fft.Domain.
+// Memory layout is gnark's: 4 x u64 little-endian limbs, Montgomery form, R = 2^256, fully reduced (< modulus).
+// In registers an element is 8 x u32.  The multiplier is a CIOS interleave written as two carry chains of
+// IMAD.WIDE.U32(.X) per step: "even" products a[0,2,4,6]*b_i tile 64-bit slots aligned at bit 0, "odd" products
+// a[1,3,5,7]*b_i tile slots aligned at bit 32, so no product ever straddles an accumulator boundary and every
+// 32x32 product is exactly one IMAD.WIDE with the carry travelling in a predicate (ptxas fuses
+// mad.lo.cc/madc.hi.cc pairs).  136 IMAD per multiplication, ~30 IADD3 on the other pipe.
+#pragma once
+#include <cstdint>
+
+namespace b200zk {
+
+struct FrParams {
+  // r = 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001
+  static constexpr uint32_t M0 = 0xf0000001u, M1 = 0x43e1f593u, M2 = 0x79b97091u, M3 = 0x2833e848u,
+                            M4 = 0x8181585du, M5 = 0xb85045b6u, M6 = 0xe131a029u, M7 = 0x30644e72u;
+  static constexpr uint32_t NINV = 0xefffffffu;  // -r^-1 mod 2^32
+  // R mod r
+  static __host__ __device__ __forceinline__ uint32_t one(int i) {
+    constexpr uint32_t v[8] = {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u,
+                               0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+    return v[i];
+  }
+  // R^2 mod r
+  static __host__ __device__ __forceinline__ uint32_t r2(int i) {
+    constexpr uint32_t v[8] = {0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u,
+                               0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u};
+    return v[i];
+  }
+};
+
+struct FpParams {
+  // p = 0x30644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd47
+  static constexpr uint32_t M0 = 0xd87cfd47u, M1 = 0x3c208c16u, M2 = 0x6871ca8du, M3 = 0x97816a91u,
+                            M4 = 0x8181585du, M5 = 0xb85045b6u, M6 = 0xe131a029u, M7 = 0x30644e72u;
+  static constexpr uint32_t NINV = 0xe4866389u;  // -p^-1 mod 2^32
+  static __host__ __device__ __forceinline__ uint32_t one(int i) {
+    constexpr uint32_t v[8] = {0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u,
+                               0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+    return v[i];
+  }
+  static __host__ __device__ __forceinline__ uint32_t r2(int i) {
+    constexpr uint32_t v[8] = {0x538afa89u, 0xf32cfc5bu, 0xd44501fbu, 0xb5e71911u,
+                               0x0a417ff6u, 0x47ab1effu, 0xcab8351fu, 0x06d89f71u};
+    return v[i];
+  }
+};
+
+template <class P>
+struct Fe {
+  uint32_t l[8];
+};
+using Fr = Fe<FrParams>;
+using Fp = Fe<FpParams>;
+
+// ---------------------------------------------------------------------------------------------------
+// carry-chain building blocks (each asm statement is a complete chain: the PTX carry flag never has to
+// survive between statements)
+// ---------------------------------------------------------------------------------------------------
+
+// acc[0..7] = sum_k a_k * b * 2^(64k)   (4 disjoint 64-bit products)
+__device__ __forceinline__ void mulw4(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                      uint32_t b) {
+  asm("mul.lo.u32 %0, %8, %12;\n\t"
+      "mul.hi.u32 %1, %8, %12;\n\t"
+      "mul.lo.u32 %2, %9, %12;\n\t"
+      "mul.hi.u32 %3, %9, %12;\n\t"
+      "mul.lo.u32 %4, %10, %12;\n\t"
+      "mul.hi.u32 %5, %10, %12;\n\t"
+      "mul.lo.u32 %6, %11, %12;\n\t"
+      "mul.hi.u32 %7, %11, %12;"
+      : "=r"(acc[0]), "=r"(acc[1]), "=r"(acc[2]), "=r"(acc[3]), "=r"(acc[4]), "=r"(acc[5]), "=r"(acc[6]),
+        "=r"(acc[7])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+}
+
+// acc[0..7] += sum_k a_k * b * 2^(64k); top += carry out
+__device__ __forceinline__ void madw4_top(uint32_t* acc, uint32_t& top, uint32_t a0, uint32_t a1, uint32_t a2,
+                                          uint32_t a3, uint32_t b) {
+  asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+      "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+      "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+      "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+      "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+      "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+      "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+      "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+      "addc.u32 %8, %8, 0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]),
+        "+r"(acc[7]), "+r"(top)
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+}
+
+// acc[0..7] += sum_k a_k * b * 2^(64k)   (caller guarantees no carry out)
+__device__ __forceinline__ void madw4(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                      uint32_t b) {
+  asm("mad.lo.cc.u32 %0, %8, %12, %0;\n\t"
+      "madc.hi.cc.u32 %1, %8, %12, %1;\n\t"
+      "madc.lo.cc.u32 %2, %9, %12, %2;\n\t"
+      "madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+      "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"
+      "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+      "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
+      "madc.hi.u32 %7, %11, %12, %7;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]),
+        "+r"(acc[7])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+}
+
+// carry = (x + y) >> 32 ; acc[0..7] += sum_k a_k * b * 2^(64k) + carry   (no carry out)
+__device__ __forceinline__ void madw4_cin(uint32_t* acc, uint32_t x, uint32_t y, uint32_t a0, uint32_t a1,
+                                          uint32_t a2, uint32_t a3, uint32_t b) {
+  uint32_t scratch;
+  (void)scratch;
+  asm("add.cc.u32 %8, %9, %10;\n\t"
+      "madc.lo.cc.u32 %0, %11, %15, %0;\n\t"
+      "madc.hi.cc.u32 %1, %11, %15, %1;\n\t"
+      "madc.lo.cc.u32 %2, %12, %15, %2;\n\t"
+      "madc.hi.cc.u32 %3, %12, %15, %3;\n\t"
+      "madc.lo.cc.u32 %4, %13, %15, %4;\n\t"
+      "madc.hi.cc.u32 %5, %13, %15, %5;\n\t"
+      "madc.lo.cc.u32 %6, %14, %15, %6;\n\t"
+      "madc.hi.u32 %7, %14, %15, %7;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]),
+        "+r"(acc[7]), "=r"(scratch)
+      : "r"(x), "r"(y), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+}
+
+// r = a + b (8 limbs), returns nothing: inputs < 2^255 so no carry out
+__device__ __forceinline__ void add8(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  asm("add.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32 %7, %15, %23;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]),
+        "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+}
+
+// r = a - b (8 limbs); returns borrow mask (0xffffffff if a < b else 0)
+__device__ __forceinline__ uint32_t sub8(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  uint32_t borrow;
+  asm("sub.cc.u32 %0, %9, %17;\n\t"
+      "subc.cc.u32 %1, %10, %18;\n\t"
+      "subc.cc.u32 %2, %11, %19;\n\t"
+      "subc.cc.u32 %3, %12, %20;\n\t"
+      "subc.cc.u32 %4, %13, %21;\n\t"
+      "subc.cc.u32 %5, %14, %22;\n\t"
+      "subc.cc.u32 %6, %15, %23;\n\t"
+      "subc.cc.u32 %7, %16, %24;\n\t"
+      "subc.u32 %8, 0, 0;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(borrow)
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]),
+        "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+  return borrow;
+}
+
+template <class P>
+__device__ __forceinline__ void load_mod(uint32_t* m) {
+  m[0] = P::M0; m[1] = P::M1; m[2] = P::M2; m[3] = P::M3;
+  m[4] = P::M4; m[5] = P::M5; m[6] = P::M6; m[7] = P::M7;
+}
+
+// if x >= modulus: x -= modulus      (x < 2*modulus)
+template <class P>
+__device__ __forceinline__ void final_sub(uint32_t* x) {
+  uint32_t m[8], t[8];
+  load_mod<P>(m);
+  uint32_t borrow = sub8(t, x, m);
+#pragma unroll
+  for (int i = 0; i < 8; i++) x[i] = borrow ? x[i] : t[i];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// field operations
+// ---------------------------------------------------------------------------------------------------
+template <class P>
+__device__ __forceinline__ Fe<P> fe_zero() {
+  Fe<P> r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.l[i] = 0;
+  return r;
+}
+
+template <class P>
+__device__ __forceinline__ Fe<P> fe_one() {
+  Fe<P> r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.l[i] = P::one(i);
+  return r;
+}
+
+template <class P>
+__device__ __forceinline__ bool fe_is_zero(const Fe<P>& a) {
+  uint32_t o = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) o |= a.l[i];
+  return o == 0;
+}
+
+template <class P>
+__device__ __forceinline__ bool fe_eq(const Fe<P>& a, const Fe<P>& b) {
+  uint32_t o = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) o |= a.l[i] ^ b.l[i];
+  return o == 0;
+}
+
+template <class P>
+__device__ __forceinline__ Fe<P> fe_add(const Fe<P>& a, const Fe<P>& b) {
+  Fe<P> r;
+  add8(r.l, a.l, b.l);
+  final_sub<P>(r.l);
+  return r;
+}
+
+template <class P>
+__device__ __forceinline__ Fe<P> fe_sub(const Fe<P>& a, const Fe<P>& b) {
+  Fe<P> r;
+  uint32_t m[8];
+  load_mod<P>(m);
+  uint32_t borrow = sub8(r.l, a.l, b.l);
+#pragma unroll
+  for (int i = 0; i < 8; i++) m[i] &= borrow;
+  add8(r.l, r.l, m);
+  return r;
+}
+
+template <class P>
+__device__ __forceinline__ Fe<P> fe_neg(const Fe<P>& a) {
+  Fe<P> r;
+  uint32_t m[8];
+  load_mod<P>(m);
+  sub8(r.l, m, a.l);
+  bool z = fe_is_zero(a);
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.l[i] = z ? 0u : r.l[i];
+  return r;
+}
+
+template <class P>
+__device__ __forceinline__ Fe<P> fe_dbl(const Fe<P>& a) {
+  return fe_add(a, a);
+}
+
+// Montgomery product a*b/R mod modulus, fully reduced.
+template <class P>
+__device__ __forceinline__ Fe<P> fe_mul(const Fe<P>& a, const Fe<P>& b) {
+  uint32_t E[8], O[8], top, c;
+  // step 0
+  mulw4(E, a.l[0], a.l[2], a.l[4], a.l[6], b.l[0]);
+  mulw4(O, a.l[1], a.l[3], a.l[5], a.l[7], b.l[0]);
+  top = 0;
+  {
+    uint32_t q = E[0] * P::NINV;
+    madw4_top(E, top, P::M0, P::M2, P::M4, P::M6, q);
+    // E[0] == 0 here, no pending limb: plain chain
+    madw4(O, P::M1, P::M3, P::M5, P::M7, q);
+  }
+  // shift by one limb: T/2^32 = O + (E >> 32); E[1] stays pending in c
+  c = E[1];
+  {
+    uint32_t nO[8] = {E[2], E[3], E[4], E[5], E[6], E[7], top, 0u};
+#pragma unroll
+    for (int k = 0; k < 8; k++) { E[k] = O[k]; O[k] = nO[k]; }
+  }
+#pragma unroll
+  for (int i = 1; i < 8; i++) {
+    top = 0;
+    madw4_top(E, top, a.l[0], a.l[2], a.l[4], a.l[6], b.l[i]);
+    madw4(O, a.l[1], a.l[3], a.l[5], a.l[7], b.l[i]);
+    uint32_t q = (E[0] + c) * P::NINV;
+    madw4_top(E, top, P::M0, P::M2, P::M4, P::M6, q);
+    // (E[0] + c) == 0 mod 2^32: its carry has weight 2^32 = limb 0 of the odd accumulator
+    madw4_cin(O, E[0], c, P::M1, P::M3, P::M5, P::M7, q);
+    c = E[1];
+    uint32_t nO[8] = {E[2], E[3], E[4], E[5], E[6], E[7], top, 0u};
+#pragma unroll
+    for (int k = 0; k < 8; k++) { E[k] = O[k]; O[k] = nO[k]; }
+  }
+  // result = E + c + 2^32 * O
+  Fe<P> r;
+  asm("add.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32 %7, %15, %23;"
+      : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]),
+        "=r"(r.l[7])
+      : "r"(E[0]), "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(c), "r"(O[0]),
+        "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]));
+  final_sub<P>(r.l);
+  return r;
+}
+
+template <class P>
+__device__ __forceinline__ Fe<P> fe_sqr(const Fe<P>& a) {
+  return fe_mul(a, a);
+}
+
+// Montgomery form -> regular integer (multiply by 1)
+template <class P>
+__device__ __forceinline__ Fe<P> fe_from_mont(const Fe<P>& a) {
+  Fe<P> one;
+#pragma unroll
+  for (int i = 0; i < 8; i++) one.l[i] = (i == 0) ? 1u : 0u;
+  return fe_mul(a, one);
+}
+
+template <class P>
+__device__ __forceinline__ Fe<P> fe_to_mont(const Fe<P>& a) {
+  Fe<P> r2;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r2.l[i] = P::r2(i);
+  return fe_mul(a, r2);
+}
+
+// a^(modulus-2): Fermat inversion, 4-bit fixed window.  inv(0) = 0 (gnark's Inverse convention).
+template <class P>
+__device__ __noinline__ Fe<P> fe_inv(const Fe<P>& a) {
+  uint32_t e[8];
+  load_mod<P>(e);
+  e[0] -= 2;  // both moduli end in ...01 / ...47: no borrow
+  Fe<P> tab[16];
+  tab[0] = fe_one<P>();
+  tab[1] = a;
+  for (int i = 2; i < 16; i++) tab[i] = fe_mul(tab[i - 1], a);
+  Fe<P> acc = fe_one<P>();
+  for (int i = 7; i >= 0; i--) {
+    for (int j = 28; j >= 0; j -= 4) {
+      acc = fe_sqr(acc);
+      acc = fe_sqr(acc);
+      acc = fe_sqr(acc);
+      acc = fe_sqr(acc);
+      uint32_t d = (e[i] >> j) & 15u;
+      acc = fe_mul(acc, tab[d]);
+    }
+  }
+  return acc;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// global memory access: one element = 32 bytes = two 16-byte vectors
+// ---------------------------------------------------------------------------------------------------
+template <class P>
+__device__ __forceinline__ Fe<P> fe_load(const void* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 lo = q[0], hi = q[1];
+  Fe<P> r;
+  r.l[0] = lo.x; r.l[1] = lo.y; r.l[2] = lo.z; r.l[3] = lo.w;
+  r.l[4] = hi.x; r.l[5] = hi.y; r.l[6] = hi.z; r.l[7] = hi.w;
+  return r;
+}
+
+template <class P>
+__device__ __forceinline__ Fe<P> fe_load_ro(const void* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 lo = __ldg(q), hi = __ldg(q + 1);
+  Fe<P> r;
+  r.l[0] = lo.x; r.l[1] = lo.y; r.l[2] = lo.z; r.l[3] = lo.w;
+  r.l[4] = hi.x; r.l[5] = hi.y; r.l[6] = hi.z; r.l[7] = hi.w;
+  return r;
+}
+
+template <class P>
+__device__ __forceinline__ void fe_store(void* p, const Fe<P>& a) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+  q[0] = make_uint4(a.l[0], a.l[1], a.l[2], a.l[3]);
+  q[1] = make_uint4(a.l[4], a.l[5], a.l[6], a.l[7]);
+}
+
+}  // namespace b200zk

@@ -1,0 +1,326 @@
+// fr NTT for sm_100a: replaces gnark-crypto v0.9.1 ecc/bn254/fr/fft (Domain.FFT / FFTInverse / BitReverse),
+// reached in the reference from plonk.Prove / plonk.Setup
+// (/root/reference/gnark_backend_ffi/backend/plonk/plonk.go:67, :21).
+//
+// Structure: the log2(N) radix-2 stages are grouped into passes of k <= 8..10 stages.  One CTA stages a tile of
+// 2^k "rows" x 2^cb contiguous "columns" through shared memory, runs the k stages there, and writes the tile
+// back; a transform is ceil(log2 N / k) passes over HBM.  Twiddles come from one full table w^i (i < N/2) per
+// domain and direction, so a butterfly costs exactly one Montgomery multiplication (the kernel is bound by the
+// integer multiplier, not by HBM: see DESIGN.md).  Coset pre-scaling (5^i), the 1/n post-scaling and the coset
+// post-scaling (5^-i / n) are fused into the first / last pass; 5^e is formed from a two-level table.
+#include "common.cuh"
+#include "consts.cuh"
+#include "field.cuh"
+
+namespace b200zk {
+
+static constexpr int COSET_LO_BITS = 12;
+
+// ---------------------------------------------------------------------------------------------------
+// domain setup
+// ---------------------------------------------------------------------------------------------------
+struct DomainSeeds {
+  // pw[d][k] = base_d^(2^k): d = 0 w, 1 w^-1, 2 coset, 3 coset^-1
+  Fr pw[4][32];
+  Fr ninv;
+};
+
+__global__ void ntt_seed_kernel(DomainSeeds* out, unsigned log2n) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  Fr w, wi, g, gi, h;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    w.l[i] = FR_ROOT28[i];
+    wi.l[i] = FR_ROOT28_INV[i];
+    g.l[i] = FR_COSET[i];
+    gi.l[i] = FR_COSET_INV[i];
+    h.l[i] = FR_INV2[i];
+  }
+  for (unsigned k = log2n; k < B200ZK_MAX_LOG2N; k++) {
+    w = fe_sqr(w);
+    wi = fe_sqr(wi);
+  }
+  Fr ninv = fe_one<FrParams>();
+  for (unsigned k = 0; k < log2n; k++) ninv = fe_mul(ninv, h);
+  out->ninv = ninv;
+  for (int k = 0; k < 32; k++) {
+    out->pw[0][k] = w;
+    out->pw[1][k] = wi;
+    out->pw[2][k] = g;
+    out->pw[3][k] = gi;
+    w = fe_sqr(w);
+    wi = fe_sqr(wi);
+    g = fe_sqr(g);
+    gi = fe_sqr(gi);
+  }
+}
+
+// table[i] = base^(i << shift) (* ninv if with_ninv), base given by its 2^k powers
+__global__ void ntt_fill_pow_kernel(uint4* table, size_t count, const DomainSeeds* seeds, int which, int shift,
+                                    int with_ninv) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  Fr acc = with_ninv ? seeds->ninv : fe_one<FrParams>();
+  size_t e = i;
+  for (int k = shift; e != 0; k++, e >>= 1) {
+    if (e & 1) acc = fe_mul(acc, seeds->pw[which][k]);
+  }
+  fe_store(table + 2 * i, acc);
+}
+
+static int build_domain(b200zk_ctx* ctx, unsigned log2n) {
+  NttDomain& d = ctx->domains[log2n];
+  if (d.ready) return B200ZK_OK;
+  const size_t N = (size_t)1 << log2n;
+  const size_t ntw = N / 2 ? N / 2 : 1;
+  const size_t nlo = (size_t)1 << (log2n < (unsigned)COSET_LO_BITS ? log2n : COSET_LO_BITS);
+  const size_t nhi = log2n > (unsigned)COSET_LO_BITS ? (size_t)1 << (log2n - COSET_LO_BITS) : 1;
+  DomainSeeds* seeds = nullptr;
+  B200ZK_CUDA(ctx, cudaMalloc(&seeds, sizeof(DomainSeeds)));
+  B200ZK_CUDA(ctx, cudaMalloc(&d.tw_fwd, ntw * 32));
+  B200ZK_CUDA(ctx, cudaMalloc(&d.tw_inv, ntw * 32));
+  B200ZK_CUDA(ctx, cudaMalloc(&d.coset_lo, nlo * 32));
+  B200ZK_CUDA(ctx, cudaMalloc(&d.coset_inv_lo, nlo * 32));
+  B200ZK_CUDA(ctx, cudaMalloc(&d.coset_hi, nhi * 32));
+  B200ZK_CUDA(ctx, cudaMalloc(&d.coset_inv_hi, nhi * 32));
+  B200ZK_CUDA(ctx, cudaMalloc(&d.scalars, 32));
+  ntt_seed_kernel<<<1, 32, 0, ctx->stream>>>(seeds, log2n);
+  B200ZK_LAUNCH_CHECK(ctx, "ntt_seed_kernel");
+  auto fill = [&](void* t, size_t cnt, int which, int shift, int with_ninv) -> int {
+    unsigned blocks = (unsigned)((cnt + 255) / 256);
+    ntt_fill_pow_kernel<<<blocks, 256, 0, ctx->stream>>>((uint4*)t, cnt, seeds, which, shift, with_ninv);
+    B200ZK_LAUNCH_CHECK(ctx, "ntt_fill_pow_kernel");
+    return B200ZK_OK;
+  };
+  B200ZK_TRY(fill(d.tw_fwd, ntw, 0, 0, 0));
+  B200ZK_TRY(fill(d.tw_inv, ntw, 1, 0, 0));
+  B200ZK_TRY(fill(d.coset_lo, nlo, 2, 0, 0));
+  B200ZK_TRY(fill(d.coset_inv_lo, nlo, 3, 0, 1));
+  B200ZK_TRY(fill(d.coset_hi, nhi, 2, COSET_LO_BITS, 0));
+  B200ZK_TRY(fill(d.coset_inv_hi, nhi, 3, COSET_LO_BITS, 0));
+  B200ZK_TRY(fill(d.scalars, 1, 0, 0, 1));
+  B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  B200ZK_CUDA(ctx, cudaFree(seeds));
+  d.log2n = log2n;
+  d.ready = true;
+  return B200ZK_OK;
+}
+
+void ntt_free_domains(b200zk_ctx* ctx) {
+  for (auto& d : ctx->domains) {
+    if (!d.ready) continue;
+    cudaFree(d.tw_fwd);
+    cudaFree(d.tw_inv);
+    cudaFree(d.coset_lo);
+    cudaFree(d.coset_hi);
+    cudaFree(d.coset_inv_lo);
+    cudaFree(d.coset_inv_hi);
+    cudaFree(d.scalars);
+    d = NttDomain();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the pass kernel
+// ---------------------------------------------------------------------------------------------------
+enum ScaleMode { SCALE_NONE = 0, SCALE_PRE_COSET = 1, SCALE_POST_NINV = 2, SCALE_POST_COSET = 3 };
+
+struct PassParams {
+  unsigned n;        // log2 N
+  unsigned L;        // index bits below the row bits
+  unsigned k;        // stages in this pass = row bits
+  unsigned cb;       // column bits; tile = 2^(k+cb) elements
+  int scale;         // ScaleMode
+  int scale_bitrev;  // table index is the bit-reversed element index
+  const uint4* tw;
+  const uint4* lo;
+  const uint4* hi;
+  const uint4* ninv;
+};
+
+__device__ __forceinline__ size_t tile_to_global(const PassParams& p, size_t tile, unsigned r, unsigned c) {
+  const unsigned Lc = p.L < p.cb ? p.L : p.cb;
+  const size_t low_c = c & ((1u << Lc) - 1u);
+  const size_t high_c = c >> Lc;
+  const size_t tile_low = tile & (((size_t)1 << (p.L - Lc)) - 1);
+  const size_t tile_high = tile >> (p.L - Lc);
+  return ((tile_low << Lc) | low_c) | ((size_t)r << p.L) | (((tile_high << (p.cb - Lc)) | high_c) << (p.L + p.k));
+}
+
+__device__ __forceinline__ Fr coset_factor(const PassParams& p, size_t idx) {
+  size_t e = idx;
+  if (p.scale_bitrev) e = (size_t)(__brev((unsigned)idx) >> (32 - p.n));
+  Fr f = fe_load_ro<FrParams>(p.lo + 2 * (e & ((1u << COSET_LO_BITS) - 1u)));
+  if (p.n > (unsigned)COSET_LO_BITS) {
+    Fr h = fe_load_ro<FrParams>(p.hi + 2 * (e >> COSET_LO_BITS));
+    f = fe_mul(f, h);
+  }
+  return f;
+}
+
+// Shared layout: two planes of 16-byte half elements, so a warp's LDS.128 / STS.128 are conflict free.
+template <bool DIT>
+__global__ void __launch_bounds__(512) ntt_pass_kernel(uint4* __restrict__ a, PassParams p) {
+  extern __shared__ uint4 smem[];
+  const unsigned tlog = p.k + p.cb;
+  const unsigned T = 1u << tlog;
+  uint4* s_lo = smem;
+  uint4* s_hi = smem + T;
+  const size_t tile = blockIdx.x;
+  const unsigned nthreads = blockDim.x;  // T/2 (or 1)
+  const unsigned cmask = (1u << p.cb) - 1u;
+
+  // ---- load tile (with optional coset pre-scaling)
+  for (unsigned e = threadIdx.x; e < T; e += nthreads) {
+    const unsigned r = e >> p.cb, c = e & cmask;
+    const size_t g = tile_to_global(p, tile, r, c);
+    Fr v = fe_load<FrParams>(a + 2 * g);
+    if (p.scale == SCALE_PRE_COSET) v = fe_mul(v, coset_factor(p, g));
+    s_lo[e] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    s_hi[e] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+  }
+  __syncthreads();
+
+  // ---- k radix-2 stages in shared memory
+  for (unsigned t = 0; t < p.k; t++) {
+    // DIF walks row distance 2^(k-1) .. 1, DIT walks 1 .. 2^(k-1)
+    const unsigned dbit = DIT ? t : (p.k - 1 - t);
+    const unsigned hbit = p.L + dbit;  // global half-distance = 2^hbit
+    for (unsigned b = threadIdx.x; b < T / 2; b += nthreads) {
+      const unsigned c = b & cmask;
+      const unsigned rb = b >> p.cb;
+      const unsigned r0 = ((rb >> dbit) << (dbit + 1)) | (rb & ((1u << dbit) - 1u));
+      const unsigned r1 = r0 | (1u << dbit);
+      const unsigned e0 = (r0 << p.cb) | c, e1 = (r1 << p.cb) | c;
+      Fr u, v;
+      {
+        uint4 x = s_lo[e0], y = s_hi[e0];
+        u.l[0] = x.x; u.l[1] = x.y; u.l[2] = x.z; u.l[3] = x.w;
+        u.l[4] = y.x; u.l[5] = y.y; u.l[6] = y.z; u.l[7] = y.w;
+        x = s_lo[e1]; y = s_hi[e1];
+        v.l[0] = x.x; v.l[1] = x.y; v.l[2] = x.z; v.l[3] = x.w;
+        v.l[4] = y.x; v.l[5] = y.y; v.l[6] = y.z; v.l[7] = y.w;
+      }
+      const size_t g0 = tile_to_global(p, tile, r0, c);
+      const size_t j = g0 & (((size_t)1 << hbit) - 1);
+      const size_t ex = j << (p.n - 1 - hbit);  // exponent of w, < N/2
+      Fr x0, x1;
+      if (DIT) {
+        if (hbit != 0) v = fe_mul(v, fe_load_ro<FrParams>(p.tw + 2 * ex));
+        x0 = fe_add(u, v);
+        x1 = fe_sub(u, v);
+      } else {
+        x0 = fe_add(u, v);
+        x1 = fe_sub(u, v);
+        if (hbit != 0) x1 = fe_mul(x1, fe_load_ro<FrParams>(p.tw + 2 * ex));
+      }
+      s_lo[e0] = make_uint4(x0.l[0], x0.l[1], x0.l[2], x0.l[3]);
+      s_hi[e0] = make_uint4(x0.l[4], x0.l[5], x0.l[6], x0.l[7]);
+      s_lo[e1] = make_uint4(x1.l[0], x1.l[1], x1.l[2], x1.l[3]);
+      s_hi[e1] = make_uint4(x1.l[4], x1.l[5], x1.l[6], x1.l[7]);
+    }
+    __syncthreads();
+  }
+
+  // ---- store tile (with optional post-scaling)
+  for (unsigned e = threadIdx.x; e < T; e += nthreads) {
+    const unsigned r = e >> p.cb, c = e & cmask;
+    const size_t g = tile_to_global(p, tile, r, c);
+    uint4 x = s_lo[e], y = s_hi[e];
+    Fr v;
+    v.l[0] = x.x; v.l[1] = x.y; v.l[2] = x.z; v.l[3] = x.w;
+    v.l[4] = y.x; v.l[5] = y.y; v.l[6] = y.z; v.l[7] = y.w;
+    if (p.scale == SCALE_POST_NINV) v = fe_mul(v, fe_load_ro<FrParams>(p.ninv));
+    if (p.scale == SCALE_POST_COSET) v = fe_mul(v, coset_factor(p, g));
+    fe_store(a + 2 * g, v);
+  }
+}
+
+__global__ void bit_reverse_kernel(uint4* a, unsigned log2n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >> log2n) return;
+  size_t j = (size_t)(__brev((unsigned)i) >> (32 - log2n));
+  if (i < j) {
+    uint4 x0 = a[2 * i], x1 = a[2 * i + 1];
+    uint4 y0 = a[2 * j], y1 = a[2 * j + 1];
+    a[2 * i] = y0; a[2 * i + 1] = y1;
+    a[2 * j] = x0; a[2 * j + 1] = x1;
+  }
+}
+
+int bit_reverse_run(b200zk_ctx* ctx, void* a_dev, unsigned log2n) {
+  if (log2n == 0) return B200ZK_OK;
+  size_t N = (size_t)1 << log2n;
+  unsigned blocks = (unsigned)((N + 255) / 256);
+  bit_reverse_kernel<<<blocks, 256, 0, ctx->stream>>>((uint4*)a_dev, log2n);
+  B200ZK_LAUNCH_CHECK(ctx, "bit_reverse_kernel");
+  return B200ZK_OK;
+}
+
+static constexpr unsigned TILE_LOG = 10;   // 1024 elements = 32 KiB shared memory per CTA
+static constexpr unsigned MIN_CB = 2;      // >= 4 contiguous elements (128 B) per row segment
+
+int ntt_run(b200zk_ctx* ctx, void* a_dev, unsigned log2n, int inverse, int decimation, int coset) {
+  if (log2n > B200ZK_MAX_LOG2N) return B200ZK_ERR_BAD_ARG;
+  if (log2n == 0) return B200ZK_OK;
+  B200ZK_TRY(build_domain(ctx, log2n));
+  const NttDomain& d = ctx->domains[log2n];
+  const bool dit = decimation == B200ZK_DIT;
+
+  // split the stages into passes
+  unsigned npass, ks[8];
+  if (log2n <= TILE_LOG) {
+    npass = 1;
+    ks[0] = log2n;
+  } else {
+    const unsigned kmax = TILE_LOG - MIN_CB;
+    npass = (log2n + kmax - 1) / kmax;
+    unsigned base = log2n / npass, rem = log2n % npass;
+    for (unsigned i = 0; i < npass; i++) ks[i] = base + (i < rem ? 1 : 0);
+  }
+  unsigned done = 0;  // stages already executed
+  for (unsigned pi = 0; pi < npass; pi++) {
+    PassParams p;
+    p.n = log2n;
+    p.k = ks[pi];
+    // DIF: stages from the top (largest distance first); DIT: from the bottom
+    p.L = dit ? done : (log2n - done - p.k);
+    const unsigned tlog = log2n < TILE_LOG ? log2n : TILE_LOG;
+    p.cb = tlog - p.k;
+    p.tw = (const uint4*)(inverse ? d.tw_inv : d.tw_fwd);
+    p.lo = p.hi = nullptr;
+    p.ninv = (const uint4*)d.scalars;
+    p.scale = SCALE_NONE;
+    p.scale_bitrev = 0;
+    if (!inverse && coset && pi == 0) {
+      p.scale = SCALE_PRE_COSET;
+      p.lo = (const uint4*)d.coset_lo;
+      p.hi = (const uint4*)d.coset_hi;
+      p.scale_bitrev = dit ? 1 : 0;  // DIT input is in bit-reversed order
+    }
+    if (inverse && pi == npass - 1) {
+      if (coset) {
+        p.scale = SCALE_POST_COSET;
+        p.lo = (const uint4*)d.coset_inv_lo;
+        p.hi = (const uint4*)d.coset_inv_hi;
+        p.scale_bitrev = dit ? 0 : 1;  // DIF output is in bit-reversed order
+      } else {
+        p.scale = SCALE_POST_NINV;
+      }
+    }
+    const unsigned T = 1u << tlog;
+    const unsigned threads = T / 2 ? T / 2 : 1;
+    const unsigned tiles = (unsigned)(((size_t)1 << log2n) >> tlog);
+    const size_t shmem = (size_t)T * 32;
+    PhaseTimer pt(ctx, PH_NTT_PASS);
+    if (dit)
+      ntt_pass_kernel<true><<<tiles, threads, shmem, ctx->stream>>>((uint4*)a_dev, p);
+    else
+      ntt_pass_kernel<false><<<tiles, threads, shmem, ctx->stream>>>((uint4*)a_dev, p);
+    B200ZK_LAUNCH_CHECK(ctx, "ntt_pass_kernel");
+    done += p.k;
+  }
+  return B200ZK_OK;
+}
+
+}  // namespace b200zk

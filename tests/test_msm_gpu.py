@@ -1,0 +1,174 @@
+"""GPU parity: b200zk_msm_g1 == (*G1Affine).MultiExp (canonical affine result, bit-exact), through the C ABI."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import noir_backend_using_gnark_b200 as zk
+from oracle import bn254 as o
+from oracle import cref
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def gen_point(k: int) -> bytes:
+    return o.g1_to_bytes([o.g1_mul(o.G1_GEN, k)])
+
+
+def structured(n: int, a: int = 0xB2000002 % 9973, b: int = 7919) -> np.ndarray:
+    """P_i = (a + i*b)*G (SURVEY.md §8c self-checking bases)."""
+    return cref.g1_arith_progression(gen_point(a), gen_point(b), n)
+
+
+def closed_form(scalars_mont: np.ndarray, n: int, a: int = 0xB2000002 % 9973, b: int = 7919) -> bytes:
+    s = o.fr_from_mont_bytes(scalars_mont[: n * 32].tobytes())
+    k = sum(si * (a + i * b) for i, si in enumerate(s)) % o.R_MOD
+    return o.g1_to_bytes([o.g1_mul(o.G1_GEN, k)])
+
+
+def test_golden_vectors(ctx):
+    with open(os.path.join(GOLDEN, "msm_small.json")) as f:
+        for v in json.load(f):
+            srs = zk.SRS(bytes.fromhex(v["points"]), ctx)
+            got = zk.MultiExp(srs, bytes.fromhex(v["scalars"]))
+            assert got.hex() == v["out"], v["n"]
+            srs.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 32, 33, 100, 1000, 4097])
+def test_small_sizes_vs_oracle(ctx, n):
+    pts = structured(n)
+    sc = cref.random_fr(n, 0xB2000001 + n)
+    srs = zk.SRS(pts, ctx)
+    want = cref.msm(pts, sc, n, nthreads=4)
+    assert zk.MultiExp(srs, sc) == want
+    assert want == closed_form(sc, n)
+    srs.close()
+
+
+def test_empty_and_prefix(ctx):
+    pts = structured(64)
+    sc = cref.random_fr(64, 3)
+    srs = zk.SRS(pts, ctx)
+    assert zk.MultiExp(srs, sc[:0], n=0) == b"\0" * 64           # empty sum = infinity = (0,0)
+    assert zk.MultiExp(srs, sc, n=10) == cref.msm(pts, sc, 10)   # kzg.Commit uses a prefix of the SRS
+    lib = zk.load()
+    out = np.zeros(64, dtype=np.uint8)
+    assert lib.b200zk_msm_g1(ctx.handle, srs.handle, sc.ctypes.data, 65, out.ctypes.data) == -3  # n > len(bases)
+    srs.close()
+
+
+def test_special_scalars_and_points(ctx):
+    n = 600
+    pts = structured(n).copy()
+    pts[5 * 64 : 6 * 64] = 0                       # infinity among the bases
+    pts[9 * 64 : 10 * 64] = pts[8 * 64 : 9 * 64]   # duplicate point
+    vals = o.random_fr(n, 17)
+    vals[0] = 0
+    vals[1] = 1
+    vals[2] = o.R_MOD - 1
+    vals[3] = (1 << 253) % o.R_MOD
+    vals[8] = vals[9]                              # same point, same scalar: exercises the doubling path
+    vals[20] = 1 << 15                             # digit exactly 2^(c-1) for c = 16
+    sc = np.frombuffer(o.fr_to_mont_bytes(vals), dtype=np.uint8)
+    srs = zk.SRS(pts, ctx)
+    want = cref.msm(pts, sc, n, nthreads=4)
+    for c in (0, 6, 9, 13, 16):
+        zk.load().b200zk_msm_set_window(ctx.handle, c)
+        assert zk.MultiExp(srs, sc) == want, c
+    zk.load().b200zk_msm_set_window(ctx.handle, 0)
+    # all-zero scalars -> infinity
+    assert zk.MultiExp(srs, np.zeros(n * 32, dtype=np.uint8)) == b"\0" * 64
+    srs.close()
+
+
+def test_cancellation_to_infinity(ctx):
+    # s*P + (r-s)*P = infinity
+    n = 2
+    p = gen_point(12345)
+    pts = np.frombuffer(p + p, dtype=np.uint8)
+    s = 0x1234567890ABCDEF1234567890ABCDEF
+    sc = np.frombuffer(o.fr_to_mont_bytes([s, o.R_MOD - s]), dtype=np.uint8)
+    srs = zk.SRS(pts, ctx)
+    assert zk.MultiExp(srs, sc) == b"\0" * 64
+    srs.close()
+
+
+@pytest.mark.parametrize("kind", ["all_equal", "witness_like", "same_point"])
+def test_skewed_inputs(ctx, kind):
+    """Bucket skew (SURVEY.md §8d adversarial sets): long runs go through the cooperative path."""
+    n = 1 << 15
+    pts = structured(n)
+    if kind == "all_equal":
+        v = o.random_fr(1, 5)[0]
+        sc = np.tile(np.frombuffer(o.fr_to_mont_bytes([v]), dtype=np.uint8), n)
+    elif kind == "witness_like":
+        rnd = o.random_fr(n // 4, 6)
+        vals = [0] * (n // 2) + [x % (1 << 16) for x in rnd] + rnd
+        sc = np.frombuffer(o.fr_to_mont_bytes(vals), dtype=np.uint8)
+    else:
+        pts = np.tile(np.frombuffer(gen_point(777), dtype=np.uint8), n)
+        sc = cref.random_fr(n, 8)
+    srs = zk.SRS(pts, ctx)
+    want = cref.msm(pts, sc, n, nthreads=cref.ncores())
+    for c in (0, 8):
+        zk.load().b200zk_msm_set_window(ctx.handle, c)
+        assert zk.MultiExp(srs, sc) == want, (kind, c)
+    zk.load().b200zk_msm_set_window(ctx.handle, 0)
+    srs.close()
+
+
+@pytest.mark.parametrize("log2n", [16, 18])
+def test_vs_c_oracle_medium(ctx, log2n):
+    n = 1 << log2n
+    pts = structured(n)
+    sc = cref.random_fr(n, 0xB2000001)
+    srs = zk.SRS(pts, ctx)
+    want = cref.msm(pts, sc, n, nthreads=cref.ncores())
+    assert zk.MultiExp(srs, sc) == want
+    srs.close()
+
+
+@pytest.mark.parametrize("log2n", [20, 22])
+def test_closed_form_large(ctx, log2n):
+    """Size-independent check: with P_i = (a+i*b)G the MSM must equal ((sum s_i (a+i*b)) mod r) * G."""
+    import torch
+
+    n = 1 << log2n
+    pts = structured(n)
+    sc = cref.random_fr(n, 0xB2000001 + log2n)
+    srs = zk.SRS(pts, ctx)
+    want = closed_form(sc, n)
+    assert zk.MultiExp(srs, sc) == want
+    # device-resident + sharded: two half-range partials combined == single result
+    d_sc = torch.from_numpy(sc).cuda()
+    torch.cuda.synchronize()
+    half = n // 2
+    parts = torch.empty(256, dtype=torch.uint8, device="cuda")
+    zk.MultiExp(srs, d_sc[: half * 32], n=half, first_base=0, out=parts[:128], partial=True)
+    zk.MultiExp(srs, d_sc[half * 32 :], n=half, first_base=half, out=parts[128:], partial=True)
+    res = zk.SumPartials(ctx, parts)
+    ctx.sync()
+    assert res.cpu().numpy().tobytes() == want
+    srs.close()
+
+
+def test_srs_generate_matches_oracle(ctx):
+    """kzg.NewSRS on the device: G1[i] = alpha^i * G; and Commit(p) == p(alpha) * G."""
+    alpha = o.random_fr(1, 0xB2000005)[0]
+    amont = o.fr_to_mont_bytes([alpha])
+    n = 70
+    srs = zk.SRS.NewSRS(n, amont, ctx)
+    got = o.g1_from_bytes(srs.download())
+    want = [o.g1_mul(o.G1_GEN, pow(alpha, i, o.R_MOD)) for i in range(n)]
+    assert got == want
+    shard = zk.SRS.NewSRS(10, amont, ctx, first=60)
+    assert o.g1_from_bytes(shard.download()) == want[60:70]
+    coeffs = o.random_fr(n, 4)
+    com = zk.Commit(np.frombuffer(o.fr_to_mont_bytes(coeffs), dtype=np.uint8), srs)
+    p_alpha = sum(c * pow(alpha, i, o.R_MOD) for i, c in enumerate(coeffs)) % o.R_MOD
+    assert com == o.g1_to_bytes([o.g1_mul(o.G1_GEN, p_alpha)])
+    srs.close()
+    shard.close()
