@@ -247,10 +247,10 @@ __global__ void __launch_bounds__(128) msm_reduce_l2_kernel(const void* __restri
 // ---------------------------------------------------------------------------------------------------
 // 6. window sums + Horner + normalisation
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) msm_final_kernel(const void* __restrict__ asum, const void* __restrict__ run2,
+__global__ void __launch_bounds__(64) msm_final_kernel(const void* __restrict__ asum, const void* __restrict__ run2,
                                                        const void* __restrict__ acc2, unsigned n2_per_window, MsmShape sh,
                                                        void* __restrict__ out, int out_kind) {
-  __shared__ G1XYZZ wsum[32];
+  __shared__ G1XYZZ wsum[64];  // W <= 43 (c >= 6)
   const unsigned w = threadIdx.x;
   if (w < sh.W) {
     G1XYZZ A = g1_xyzz_inf(), Bs = g1_xyzz_inf(), run = g1_xyzz_inf(), C = g1_xyzz_inf();
@@ -435,7 +435,7 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
   }
   {
     PhaseTimer pt(ctx, PH_MSM_FINAL);
-    msm_final_kernel<<<1, 32, 0, st>>>(asum, run2, acc2, n2, sh, out_dev, out_kind);
+    msm_final_kernel<<<1, 64, 0, st>>>(asum, run2, acc2, n2, sh, out_dev, out_kind);
     B200ZK_LAUNCH_CHECK(ctx, "msm_final_kernel");
   }
   return B200ZK_OK;
