@@ -63,6 +63,17 @@ uint64_t b200zk_launch_count(const b200zk_ctx* ctx);
  * device and only enqueues work on the context stream. */
 int b200zk_ntt(b200zk_ctx* ctx, void* a_host, unsigned log2n, int inverse, int decimation, int coset);
 int b200zk_ntt_dev(b200zk_ctx* ctx, void* a_dev, unsigned log2n, int inverse, int decimation, int coset);
+/* One half of the multi-GPU four-step transform of 2^log2n points over g = 2^log2g ranks (NTTs >= 2^24; the
+ * caller performs the all-to-all between the halves, see noir_backend_using_gnark_b200/dist_ntt.py).  The logical
+ * vector is viewed as R x C (C = 2^log2c).  Shard layouts (2^(log2n-log2g) elements each):
+ *   column-block  X[r][c_lo]         logical index r*C + rank*(C/g) + c_lo      (DIF input, DIT output)
+ *   row-block     Y[r_lo][c]         logical index (rank*(R/g) + r_lo)*C + c    (DIF output, DIT input)
+ *   exchange      Z[peer][r_lo][c_lo]  what all_to_all_single delivers / expects on the row-block side
+ * DIF: half 0 in place on X (src == dst); all_to_all(Z <- X); half 1 reads Z (src), writes Y (dst).
+ * DIT: half 0 works in place on Y (src) and writes Z (dst); all_to_all(X <- Z); half 1 in place on X.
+ * Same inverse / coset semantics as b200zk_ntt (scalings are applied in the half that owns the first / last stage). */
+int b200zk_ntt_dist_half_dev(b200zk_ctx* ctx, const void* src_dev, void* dst_dev, unsigned log2n, unsigned log2g,
+                             unsigned rank, unsigned log2c, int half, int inverse, int decimation, int coset);
 /* fft.BitReverse(a): in-place index bit-reversal permutation. */
 int b200zk_bit_reverse(b200zk_ctx* ctx, void* a_host, unsigned log2n);
 int b200zk_bit_reverse_dev(b200zk_ctx* ctx, void* a_dev, unsigned log2n);

@@ -118,6 +118,14 @@ int b200zk_ntt(b200zk_ctx* ctx, void* a_host, unsigned log2n, int inverse, int d
   return B200ZK_OK;
 }
 
+int b200zk_ntt_dist_half_dev(b200zk_ctx* ctx, const void* src_dev, void* dst_dev, unsigned log2n, unsigned log2g,
+                             unsigned rank, unsigned log2c, int half, int inverse, int decimation, int coset) {
+  B200ZK_TRY(enter(ctx));
+  if (!src_dev || !dst_dev || (half != 0 && half != 1) || (decimation != B200ZK_DIF && decimation != B200ZK_DIT))
+    return B200ZK_ERR_BAD_ARG;
+  return ntt_dist_run(ctx, src_dev, dst_dev, log2n, log2g, rank, log2c, half, inverse != 0, decimation, coset != 0);
+}
+
 int b200zk_bit_reverse_dev(b200zk_ctx* ctx, void* a_dev, unsigned log2n) {
   B200ZK_TRY(enter(ctx));
   if (!a_dev || log2n > B200ZK_MAX_LOG2N) return B200ZK_ERR_BAD_ARG;

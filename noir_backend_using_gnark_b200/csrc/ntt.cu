@@ -125,26 +125,49 @@ void ntt_free_domains(b200zk_ctx* ctx) {
 // ---------------------------------------------------------------------------------------------------
 enum ScaleMode { SCALE_NONE = 0, SCALE_PRE_COSET = 1, SCALE_POST_NINV = 2, SCALE_POST_COSET = 3 };
 
+// A pass works on a LOCAL array of 2^nl elements which is a slice of the logical 2^n-point vector: the logical
+// index is the local index with the `gap_bits`-wide field `gap_val` inserted at bit `gap_pos` (gap_bits = 0 on one
+// GPU; the rank id for the two halves of the multi-GPU four-step transform).  Twiddle exponents and coset powers
+// are functions of the logical index; tiles and addresses are functions of the local one.  Optionally the source
+// or destination array is stored with the bit fields [high | mid(b bits) | low(a bits)] rotated to
+// [mid | high | low] — the block layout an all-to-all delivers / expects.
 struct PassParams {
-  unsigned n;        // log2 N
-  unsigned L;        // index bits below the row bits
+  unsigned n;        // logical log2 N
+  unsigned nl;       // local log2 size
+  unsigned L;        // local index bits below the row bits
   unsigned k;        // stages in this pass = row bits
   unsigned cb;       // column bits; tile = 2^(k+cb) elements
+  unsigned gap_pos, gap_bits, gap_val;
+  unsigned perm_a, perm_b;
+  int src_perm, dst_perm;
   int scale;         // ScaleMode
-  int scale_bitrev;  // table index is the bit-reversed element index
+  int scale_bitrev;  // table index is the bit-reversed logical index
   const uint4* tw;
   const uint4* lo;
   const uint4* hi;
   const uint4* ninv;
 };
 
-__device__ __forceinline__ size_t tile_to_global(const PassParams& p, size_t tile, unsigned r, unsigned c) {
+__device__ __forceinline__ size_t tile_to_local(const PassParams& p, size_t tile, unsigned r, unsigned c) {
   const unsigned Lc = p.L < p.cb ? p.L : p.cb;
   const size_t low_c = c & ((1u << Lc) - 1u);
   const size_t high_c = c >> Lc;
   const size_t tile_low = tile & (((size_t)1 << (p.L - Lc)) - 1);
   const size_t tile_high = tile >> (p.L - Lc);
   return ((tile_low << Lc) | low_c) | ((size_t)r << p.L) | (((tile_high << (p.cb - Lc)) | high_c) << (p.L + p.k));
+}
+
+__device__ __forceinline__ size_t local_to_logical(const PassParams& p, size_t l) {
+  if (p.gap_bits == 0) return l;
+  const size_t low = l & (((size_t)1 << p.gap_pos) - 1);
+  return ((l >> p.gap_pos) << (p.gap_pos + p.gap_bits)) | ((size_t)p.gap_val << p.gap_pos) | low;
+}
+
+__device__ __forceinline__ size_t permuted(const PassParams& p, size_t l) {
+  const size_t low = l & (((size_t)1 << p.perm_a) - 1);
+  const size_t mid = (l >> p.perm_a) & (((size_t)1 << p.perm_b) - 1);
+  const size_t high = l >> (p.perm_a + p.perm_b);
+  return (mid << (p.nl - p.perm_b)) | (high << p.perm_a) | low;
 }
 
 __device__ __forceinline__ Fr coset_factor(const PassParams& p, size_t idx) {
@@ -160,7 +183,8 @@ __device__ __forceinline__ Fr coset_factor(const PassParams& p, size_t idx) {
 
 // Shared layout: two planes of 16-byte half elements, so a warp's LDS.128 / STS.128 are conflict free.
 template <bool DIT>
-__global__ void __launch_bounds__(512) ntt_pass_kernel(uint4* __restrict__ a, PassParams p) {
+__global__ void __launch_bounds__(512) ntt_pass_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst,
+                                                       PassParams p) {
   extern __shared__ uint4 smem[];
   const unsigned tlog = p.k + p.cb;
   const unsigned T = 1u << tlog;
@@ -173,9 +197,10 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(uint4* __restrict__ a, Pa
   // ---- load tile (with optional coset pre-scaling)
   for (unsigned e = threadIdx.x; e < T; e += nthreads) {
     const unsigned r = e >> p.cb, c = e & cmask;
-    const size_t g = tile_to_global(p, tile, r, c);
-    Fr v = fe_load<FrParams>(a + 2 * g);
-    if (p.scale == SCALE_PRE_COSET) v = fe_mul(v, coset_factor(p, g));
+    const size_t l = tile_to_local(p, tile, r, c);
+    const size_t addr = p.src_perm ? permuted(p, l) : l;
+    Fr v = fe_load<FrParams>(src + 2 * addr);
+    if (p.scale == SCALE_PRE_COSET) v = fe_mul(v, coset_factor(p, local_to_logical(p, l)));
     s_lo[e] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
     s_hi[e] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
   }
@@ -185,7 +210,8 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(uint4* __restrict__ a, Pa
   for (unsigned t = 0; t < p.k; t++) {
     // DIF walks row distance 2^(k-1) .. 1, DIT walks 1 .. 2^(k-1)
     const unsigned dbit = DIT ? t : (p.k - 1 - t);
-    const unsigned hbit = p.L + dbit;  // global half-distance = 2^hbit
+    const unsigned hl = p.L + dbit;                                    // local half-distance bit
+    const unsigned hbit = hl + (hl >= p.gap_pos ? p.gap_bits : 0u);    // logical half-distance = 2^hbit
     for (unsigned b = threadIdx.x; b < T / 2; b += nthreads) {
       const unsigned c = b & cmask;
       const unsigned rb = b >> p.cb;
@@ -201,7 +227,7 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(uint4* __restrict__ a, Pa
         v.l[0] = x.x; v.l[1] = x.y; v.l[2] = x.z; v.l[3] = x.w;
         v.l[4] = y.x; v.l[5] = y.y; v.l[6] = y.z; v.l[7] = y.w;
       }
-      const size_t g0 = tile_to_global(p, tile, r0, c);
+      const size_t g0 = local_to_logical(p, tile_to_local(p, tile, r0, c));
       const size_t j = g0 & (((size_t)1 << hbit) - 1);
       const size_t ex = j << (p.n - 1 - hbit);  // exponent of w, < N/2
       Fr x0, x1;
@@ -225,14 +251,15 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(uint4* __restrict__ a, Pa
   // ---- store tile (with optional post-scaling)
   for (unsigned e = threadIdx.x; e < T; e += nthreads) {
     const unsigned r = e >> p.cb, c = e & cmask;
-    const size_t g = tile_to_global(p, tile, r, c);
+    const size_t l = tile_to_local(p, tile, r, c);
     uint4 x = s_lo[e], y = s_hi[e];
     Fr v;
     v.l[0] = x.x; v.l[1] = x.y; v.l[2] = x.z; v.l[3] = x.w;
     v.l[4] = y.x; v.l[5] = y.y; v.l[6] = y.z; v.l[7] = y.w;
     if (p.scale == SCALE_POST_NINV) v = fe_mul(v, fe_load_ro<FrParams>(p.ninv));
-    if (p.scale == SCALE_POST_COSET) v = fe_mul(v, coset_factor(p, g));
-    fe_store(a + 2 * g, v);
+    if (p.scale == SCALE_POST_COSET) v = fe_mul(v, coset_factor(p, local_to_logical(p, l)));
+    const size_t addr = p.dst_perm ? permuted(p, l) : l;
+    fe_store(dst + 2 * addr, v);
   }
 }
 
@@ -260,45 +287,61 @@ int bit_reverse_run(b200zk_ctx* ctx, void* a_dev, unsigned log2n) {
 static constexpr unsigned TILE_LOG = 10;   // 1024 elements = 32 KiB shared memory per CTA
 static constexpr unsigned MIN_CB = 2;      // >= 4 contiguous elements (128 B) per row segment
 
-int ntt_run(b200zk_ctx* ctx, void* a_dev, unsigned log2n, int inverse, int decimation, int coset) {
-  if (log2n > B200ZK_MAX_LOG2N) return B200ZK_ERR_BAD_ARG;
-  if (log2n == 0) return B200ZK_OK;
-  B200ZK_TRY(build_domain(ctx, log2n));
-  const NttDomain& d = ctx->domains[log2n];
-  const bool dit = decimation == B200ZK_DIT;
+// Description of the slice of the logical transform one call works on.
+struct NttSlice {
+  unsigned n, nl;                         // logical / local log2 sizes
+  unsigned gap_pos, gap_bits, gap_val;    // logical = local with gap_val inserted at gap_pos
+  unsigned stage_lo, stage_hi;            // LOCAL half-distance bits [stage_lo, stage_hi) to execute
+  unsigned perm_a, perm_b;
+  bool src_perm, dst_perm;
+  bool first, last;                       // slice contains the first / last executed stage of the whole transform
+};
 
-  // split the stages into passes
+// Runs the stages of `sl` on src -> dst (src == dst allowed when no permutation is requested).
+static int run_slice(b200zk_ctx* ctx, const void* src, void* dst, const NttSlice& sl, int inverse, bool dit, int coset) {
+  const NttDomain& d = ctx->domains[sl.n];
+  const unsigned nstages = sl.stage_hi - sl.stage_lo;
+  const unsigned tlog = sl.nl < TILE_LOG ? sl.nl : TILE_LOG;
   unsigned npass, ks[8];
-  if (log2n <= TILE_LOG) {
+  if (nstages == 0) return B200ZK_ERR_BAD_ARG;
+  if (nstages <= tlog && (sl.stage_lo == 0 || nstages <= tlog - MIN_CB || tlog < TILE_LOG)) {
     npass = 1;
-    ks[0] = log2n;
+    ks[0] = nstages;
   } else {
     const unsigned kmax = TILE_LOG - MIN_CB;
-    npass = (log2n + kmax - 1) / kmax;
-    unsigned base = log2n / npass, rem = log2n % npass;
+    npass = (nstages + kmax - 1) / kmax;
+    unsigned base = nstages / npass, rem = nstages % npass;
     for (unsigned i = 0; i < npass; i++) ks[i] = base + (i < rem ? 1 : 0);
   }
-  unsigned done = 0;  // stages already executed
+  if ((sl.src_perm || sl.dst_perm) && src == dst) return B200ZK_ERR_BAD_ARG;
+  unsigned done = 0;
   for (unsigned pi = 0; pi < npass; pi++) {
     PassParams p;
-    p.n = log2n;
+    p.n = sl.n;
+    p.nl = sl.nl;
     p.k = ks[pi];
     // DIF: stages from the top (largest distance first); DIT: from the bottom
-    p.L = dit ? done : (log2n - done - p.k);
-    const unsigned tlog = log2n < TILE_LOG ? log2n : TILE_LOG;
+    p.L = dit ? (sl.stage_lo + done) : (sl.stage_hi - done - p.k);
     p.cb = tlog - p.k;
+    p.gap_pos = sl.gap_pos;
+    p.gap_bits = sl.gap_bits;
+    p.gap_val = sl.gap_val;
+    p.perm_a = sl.perm_a;
+    p.perm_b = sl.perm_b;
+    p.src_perm = (sl.src_perm && pi == 0) ? 1 : 0;
+    p.dst_perm = (sl.dst_perm && pi == npass - 1) ? 1 : 0;
     p.tw = (const uint4*)(inverse ? d.tw_inv : d.tw_fwd);
     p.lo = p.hi = nullptr;
     p.ninv = (const uint4*)d.scalars;
     p.scale = SCALE_NONE;
     p.scale_bitrev = 0;
-    if (!inverse && coset && pi == 0) {
+    if (!inverse && coset && sl.first && pi == 0) {
       p.scale = SCALE_PRE_COSET;
       p.lo = (const uint4*)d.coset_lo;
       p.hi = (const uint4*)d.coset_hi;
       p.scale_bitrev = dit ? 1 : 0;  // DIT input is in bit-reversed order
     }
-    if (inverse && pi == npass - 1) {
+    if (inverse && sl.last && pi == npass - 1) {
       if (coset) {
         p.scale = SCALE_POST_COSET;
         p.lo = (const uint4*)d.coset_inv_lo;
@@ -308,19 +351,84 @@ int ntt_run(b200zk_ctx* ctx, void* a_dev, unsigned log2n, int inverse, int decim
         p.scale = SCALE_POST_NINV;
       }
     }
+    // buffers: a permuted read happens on the first pass (src -> dst), a permuted write on the last one
+    // (src -> dst); every other pass is in place on whichever buffer currently holds the data
+    const void* in;
+    void* out;
+    if (sl.dst_perm) {
+      in = src;
+      out = (pi == npass - 1) ? dst : const_cast<void*>(src);
+    } else {
+      in = (pi == 0) ? src : dst;
+      out = dst;
+    }
     const unsigned T = 1u << tlog;
     const unsigned threads = T / 2 ? T / 2 : 1;
-    const unsigned tiles = (unsigned)(((size_t)1 << log2n) >> tlog);
+    const unsigned tiles = (unsigned)(((size_t)1 << sl.nl) >> tlog);
     const size_t shmem = (size_t)T * 32;
     PhaseTimer pt(ctx, PH_NTT_PASS);
     if (dit)
-      ntt_pass_kernel<true><<<tiles, threads, shmem, ctx->stream>>>((uint4*)a_dev, p);
+      ntt_pass_kernel<true><<<tiles, threads, shmem, ctx->stream>>>((const uint4*)in, (uint4*)out, p);
     else
-      ntt_pass_kernel<false><<<tiles, threads, shmem, ctx->stream>>>((uint4*)a_dev, p);
+      ntt_pass_kernel<false><<<tiles, threads, shmem, ctx->stream>>>((const uint4*)in, (uint4*)out, p);
     B200ZK_LAUNCH_CHECK(ctx, "ntt_pass_kernel");
     done += p.k;
   }
   return B200ZK_OK;
+}
+
+int ntt_run(b200zk_ctx* ctx, void* a_dev, unsigned log2n, int inverse, int decimation, int coset) {
+  if (log2n > B200ZK_MAX_LOG2N) return B200ZK_ERR_BAD_ARG;
+  if (log2n == 0) return B200ZK_OK;
+  B200ZK_TRY(build_domain(ctx, log2n));
+  NttSlice sl;
+  sl.n = sl.nl = log2n;
+  sl.gap_pos = sl.gap_bits = sl.gap_val = 0;
+  sl.stage_lo = 0;
+  sl.stage_hi = log2n;
+  sl.perm_a = sl.perm_b = 0;
+  sl.src_perm = sl.dst_perm = false;
+  sl.first = sl.last = true;
+  return run_slice(ctx, a_dev, a_dev, sl, inverse, decimation == B200ZK_DIT, coset);
+}
+
+// Multi-GPU four-step transform, one half per call (the caller performs the all-to-all between the halves).
+//   DIF: half 0 = strides >= C on the column-block shard [R][C/g] (in place); exchange;
+//        half 1 = strides < C on the row-block shard, reading the all-to-all block layout [g][R/g][C/g] from src
+//        and writing plain [R/g][C] to dst.
+//   DIT: half 0 = strides < C on the row-block shard, last pass writes the block layout to dst; exchange;
+//        half 1 = strides >= C on the column-block shard (in place).
+int ntt_dist_run(b200zk_ctx* ctx, const void* src, void* dst, unsigned log2n, unsigned log2g, unsigned rank,
+                 unsigned log2c, int half, int inverse, int decimation, int coset) {
+  if (log2n > B200ZK_MAX_LOG2N || log2g == 0 || log2c < log2g + MIN_CB || log2n < log2c + log2g || rank >> log2g)
+    return B200ZK_ERR_BAD_ARG;
+  B200ZK_TRY(build_domain(ctx, log2n));
+  const bool dit = decimation == B200ZK_DIT;
+  const unsigned nl = log2n - log2g;
+  const unsigned cl = log2c - log2g;  // log2 of local columns in the column-block shard
+  NttSlice sl;
+  sl.n = log2n;
+  sl.nl = nl;
+  sl.gap_val = rank;
+  sl.gap_bits = log2g;
+  sl.perm_a = cl;
+  sl.perm_b = log2g;
+  sl.src_perm = sl.dst_perm = false;
+  const bool high_half = dit ? (half == 1) : (half == 0);  // the half that runs strides >= C
+  if (high_half) {
+    sl.gap_pos = cl;  // column-block shard: logical = [r][rank][c_lo]
+    sl.stage_lo = cl;
+    sl.stage_hi = nl;
+  } else {
+    sl.gap_pos = nl;  // row-block shard: logical = [rank][r_lo][c]
+    sl.stage_lo = 0;
+    sl.stage_hi = log2c;
+    if (dit) sl.dst_perm = true;
+    else sl.src_perm = true;
+  }
+  sl.first = half == 0;
+  sl.last = half == 1;
+  return run_slice(ctx, src, dst, sl, inverse, dit, coset);
 }
 
 }  // namespace b200zk

@@ -127,3 +127,52 @@ def test_device_resident_roundtrip_2_24(ctx):
     ctx.sync()
     assert np.array_equal(y.cpu().numpy(), want)
     cref.load().oracle_domain_release(log2n)
+
+
+@pytest.mark.parametrize("log2n,world,log2c", [(8, 2, 4), (12, 4, 7), (14, 8, 8), (16, 2, 8), (18, 4, None)])
+def test_four_step_halves_emulated_on_one_gpu(ctx, log2n, world, log2c):
+    """Every rank's two local halves run on this one GPU; the all-to-all between them is emulated with numpy.
+    Checks the gap / block-layout addressing of b200zk_ntt_dist_half_dev for every variant."""
+    import torch
+
+    from noir_backend_using_gnark_b200.dist_ntt import ShardLayout
+
+    lay = ShardLayout(log2n, world, log2c)
+    lib = zk.load()
+    full = cref.random_fr(1 << log2n, 0xB2000003 + log2n)
+    chunk = lay.local * 32 // world
+
+    def run_half(src, dst, rank, half, inv, dec, cos):
+        rc = lib.b200zk_ntt_dist_half_dev(ctx.handle, src.data_ptr(), dst.data_ptr(), lay.log2n, lay.log2g, rank,
+                                          lay.log2c, half, inv, dec, cos)
+        assert rc == 0, rc
+
+    variants = VARIANTS if log2n <= 14 else [(0, zk.DIF, 1), (1, zk.DIT, 1), (1, zk.DIF, 0), (0, zk.DIT, 0)]
+    for inv, dec, cos in variants:
+        xs = [torch.from_numpy(lay.scatter(full, r, column_block=(dec == zk.DIF)).copy()).cuda() for r in range(world)]
+        tmps = [torch.empty_like(x) for x in xs]
+        torch.cuda.synchronize()
+        if dec == zk.DIF:
+            for r in range(world):
+                run_half(xs[r], xs[r], r, 0, inv, dec, cos)
+            ctx.sync()
+            for r in range(world):      # all_to_all_single(tmp_r, x_r): chunk j of x_k -> chunk k of tmp_j
+                for k in range(world):
+                    tmps[r][k * chunk:(k + 1) * chunk] = xs[k][r * chunk:(r + 1) * chunk]
+            torch.cuda.synchronize()
+            for r in range(world):
+                run_half(tmps[r], xs[r], r, 1, inv, dec, cos)
+        else:
+            for r in range(world):
+                run_half(xs[r], tmps[r], r, 0, inv, dec, cos)
+            ctx.sync()
+            for r in range(world):
+                for k in range(world):
+                    xs[r][k * chunk:(k + 1) * chunk] = tmps[k][r * chunk:(r + 1) * chunk]
+            torch.cuda.synchronize()
+            for r in range(world):
+                run_half(xs[r], xs[r], r, 1, inv, dec, cos)
+        ctx.sync()
+        got = lay.gather([x.cpu().numpy() for x in xs], column_block=(dec == zk.DIT))
+        want = cref.ntt(full, log2n, inv, dec, cos, cref.ncores())
+        assert got.tobytes() == want, (log2n, world, inv, dec, cos)
