@@ -108,6 +108,36 @@ int b200zk_g1_sum_dev(b200zk_ctx* ctx, const void* partials_dev, size_t count, v
 int b200zk_msm_set_window(b200zk_ctx* ctx, int c);
 
 
+/* ---- device-resident PLONK prover ----------------------------------------------------------------------
+ * The orchestration of gnark v0.8.0 plonk.Setup / plonk.Prove (called at
+ * /root/reference/gnark_backend_ffi/backend/plonk/plonk.go:21 and :67) with all polynomials resident in HBM.
+ * The host (Go shim / tests) keeps what the reference's glue computes on the CPU: the SparseR1CS rows and the wire
+ * permutation (O(n), sequential), and solving the witness.
+ *
+ * b200zk_plonk_setup: n = 2^log2n rows (placeholders for the nb_public public inputs first, then the constraints,
+ *   zero padding), big domain 2^log2n_big (gnark: 4n, or 8n when nbConstraints+nbPublic < 6).
+ *   ql..qk: selector columns in LAGRANGE form (n Montgomery fr each; ql = -1 on placeholder rows, qk = constraint
+ *   constants with zeros on placeholder rows).  permutation: gnark's pk.Permutation (3n int64).  lro: wire id of
+ *   the L | R | O column at every row (3n uint32; padding rows and the R,O of placeholder rows use wire 0).
+ *   Computes the canonical forms, S1..S3, the 8 verifying-key commitments and the Lagrange-coset forms.
+ * b200zk_plonk_vk: the 8 commitments S[0],S[1],S[2],Ql,Qr,Qm,Qo,Qk as G1Affine (64 B each).
+ * b200zk_plonk_prove: solution = value of every wire (nb_wires Montgomery fr; public wires first);
+ *   blinding = the 9 fr.SetRandom draws in gnark's order L,L,R,R,O,O,Z,Z,Z (their limbs are the Montgomery form).
+ *   proof_out (832 B) = LRO[0..2], Z, H[0..2], BatchedProof.H, ZShiftedOpening.H as G1Affine (64 B each), then
+ *   BatchedProof.ClaimedValues[0..6] and ZShiftedOpening.ClaimedValue as fr.Element (32 B each).
+ * Must be called with the context the key was set up on. */
+typedef struct b200zk_plonk_pk b200zk_plonk_pk;
+int b200zk_plonk_setup(b200zk_ctx* ctx, const b200zk_bases* bases, unsigned log2n, unsigned log2n_big,
+                       unsigned nb_public, unsigned nb_wires, const void* ql_l, const void* qr_l, const void* qm_l,
+                       const void* qo_l, const void* qk_l, const int64_t* permutation, const uint32_t* lro,
+                       b200zk_plonk_pk** out);
+void b200zk_plonk_pk_free(b200zk_ctx* ctx, b200zk_plonk_pk* pk);
+int b200zk_plonk_vk(b200zk_ctx* ctx, const b200zk_plonk_pk* pk, void* out_8_points);
+/* copy a key polynomial to the host (n fr): which = 0..8 -> Ql,Qr,Qm,Qo,CQk (canonical), LQk (Lagrange), S1,S2,S3 */
+int b200zk_plonk_pk_poly(b200zk_ctx* ctx, const b200zk_plonk_pk* pk, int which, void* out_host);
+int b200zk_plonk_prove(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solution_host, const void* blinding_host,
+                       void* proof_out);
+
 /* ---- measurement ----------------------------------------------------------------------------------------
  * Integer-pipe microbenchmarks used as roofline denominators (synchronous).  which = 0: IMAD.WIDE.U32 multiply-
  * accumulates per second; 1: fp Montgomery multiplications per second; 2: fr Montgomery multiplications per second. */

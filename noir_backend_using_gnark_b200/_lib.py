@@ -65,6 +65,11 @@ def load() -> C.CDLL:
         "b200zk_msm_g1_dev": (i, [vp, vp, sz, vp, sz, vp, i]),
         "b200zk_g1_sum_dev": (i, [vp, vp, sz, vp]),
         "b200zk_msm_set_window": (i, [vp, i]),
+        "b200zk_plonk_setup": (i, [vp, vp, u, u, u, u, vp, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]),
+        "b200zk_plonk_pk_free": (None, [vp, vp]),
+        "b200zk_plonk_vk": (i, [vp, vp, vp]),
+        "b200zk_plonk_pk_poly": (i, [vp, vp, i, vp]),
+        "b200zk_plonk_prove": (i, [vp, vp, vp, vp, vp]),
         "b200zk_microbench": (i, [vp, i, C.POINTER(C.c_double)]),
         "b200zk_profile_enable": (i, [vp, i]),
         "b200zk_profile_read": (i, [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), i]),

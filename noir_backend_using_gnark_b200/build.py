@@ -16,7 +16,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIBDIR = PKG / "lib"
 LIB = LIBDIR / "libb200zk.so"
-SOURCES = ["capi.cu", "ntt.cu", "msm.cu", "srs.cu", "microbench.cu"]
+SOURCES = ["capi.cu", "ntt.cu", "msm.cu", "srs.cu", "microbench.cu", "plonk.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -1,0 +1,262 @@
+"""Host side of the device-resident PLONK prover (C ABI: b200zk_plonk_* in include/b200zk.h).
+
+Mirrors the reference's flow for this path:
+  plonk_backend.BuildSparseR1CS  (/root/reference/gnark_backend_ffi/backend/plonk/sparse_r1cs.go:18-25, 44-107)
+  plonk.Setup                    (call site backend/plonk/plonk.go:21)   -> ProvingKey.Setup
+  plonk.Prove                    (call site backend/plonk/plonk.go:67)   -> ProvingKey.Prove
+  backend_helpers.SerializeProof (internal/backend/helpers.go:75-80)     -> Proof.to_gnark_bytes
+What stays on the CPU here is what the reference's Go glue does on the CPU: laying out the constraint rows and the
+wire permutation (O(n)); every field / curve operation on polynomials runs in libb200zk.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from .api import SRS, Context, default_context
+
+R_MOD = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+P_MOD = 0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47
+_MONT = 1 << 256
+_R_INV_R = pow(_MONT, -1, R_MOD)
+_R_INV_P = pow(_MONT, -1, P_MOD)
+
+
+def fr_to_mont(vals: Sequence[int]) -> np.ndarray:
+    """python ints -> (len*32,) uint8 in gnark's in-memory layout (Montgomery, 4 LE limbs)"""
+    return np.frombuffer(b"".join(((v % R_MOD) * _MONT % R_MOD).to_bytes(32, "little") for v in vals), dtype=np.uint8)
+
+
+def fr_from_mont(buf) -> List[int]:
+    b = bytes(buf)
+    return [int.from_bytes(b[i:i + 32], "little") * _R_INV_R % R_MOD for i in range(0, len(b), 32)]
+
+
+@dataclass
+class SparseR1CS:
+    """cs_bn254.SparseR1CS as the reference builds it: one row per arithmetic opcode,
+    qL*xa + qR*xb + qO*xc + qM*(xa*xb) + qC == 0 (sparse_r1cs.go:17)."""
+    nb_public: int
+    nb_secret: int
+    ql: List[int]
+    qr: List[int]
+    qm: List[int]
+    qo: List[int]
+    qk: List[int]
+    a: List[int]
+    b: List[int]
+    c: List[int]
+
+    @property
+    def nb_constraints(self) -> int:
+        return len(self.ql)
+
+
+def build_sparse_r1cs(acir_json: str, values: Sequence[int]):
+    """ACIR JSON + dense witness values -> (SparseR1CS, public values, secret values), bug-compatible with
+    backend.HandleValues (common.go:45-76) and handleArithmeticOpcode (sparse_r1cs.go:44-107)."""
+    d = json.loads(acir_json)
+    pubs = [int(x) for x in d["public_inputs"]]
+    public_vals, secret_vals, imap = [], [], {}
+    nb_public = nb_secret = 0
+    for i, v in enumerate(values, start=1):
+        for p in pubs:
+            if i == p:
+                imap[i] = nb_public
+                nb_public += 1
+                public_vals.append(v % R_MOD)
+    for i, v in enumerate(values, start=1):
+        if pubs:
+            for p in pubs:
+                if i != p:
+                    imap[i] = nb_public + nb_secret
+                    nb_secret += 1
+                    secret_vals.append(v % R_MOD)
+        else:
+            imap[i] = nb_public + nb_secret
+            nb_secret += 1
+            secret_vals.append(v % R_MOD)
+    cs = SparseR1CS(nb_public, nb_secret, [], [], [], [], [], [], [], [])
+    for op in d["opcodes"]:
+        if "Arithmetic" not in op:
+            if "BlackBoxFuncCall" in op or "Directive" in op:
+                continue  # no constraints (components.go:3-40, sparse_r1cs.go:36)
+            raise ValueError("unknown opcode type")
+        ar = op["Arithmetic"]
+        mul_terms, lin = ar["mul_terms"], ar["linear_combinations"]
+        xa = xb = xc = 0
+        ql = qr = qo = qm = 0
+        if mul_terms:
+            qm = int(mul_terms[0][0], 16) % R_MOD
+            xa, xb = imap.get(int(mul_terms[0][1]), 0), imap.get(int(mul_terms[0][2]), 0)
+        if len(lin) == 1:
+            qo, xc = int(lin[0][0], 16) % R_MOD, imap.get(int(lin[0][1]), 0)
+        if len(lin) == 2:
+            ql, xa = int(lin[0][0], 16) % R_MOD, imap.get(int(lin[0][1]), 0)
+            qr, xb = int(lin[1][0], 16) % R_MOD, imap.get(int(lin[1][1]), 0)
+        if len(lin) == 3:
+            ql, xa = int(lin[0][0], 16) % R_MOD, imap.get(int(lin[0][1]), 0)
+            qr, xb = int(lin[1][0], 16) % R_MOD, imap.get(int(lin[1][1]), 0)
+            qo, xc = int(lin[2][0], 16) % R_MOD, imap.get(int(lin[2][1]), 0)
+        for col, v in ((cs.ql, ql), (cs.qr, qr), (cs.qm, qm), (cs.qo, qo), (cs.qk, int(ar["q_c"], 16) % R_MOD),
+                       (cs.a, xa), (cs.b, xb), (cs.c, xc)):
+            col.append(v)
+    return cs, public_vals, secret_vals
+
+
+def _next_pow2_log(x: int) -> int:
+    n = 0
+    while (1 << n) < x:
+        n += 1
+    return n
+
+
+def build_permutation(lro: np.ndarray) -> np.ndarray:
+    """gnark buildPermutation: every position points to the previous position holding the same wire, the first
+    occurrence points to the last one (vectorised: stable sort by wire id)."""
+    order = np.argsort(lro, kind="stable")
+    w = lro[order]
+    first = np.ones(len(w), dtype=bool)
+    first[1:] = w[1:] != w[:-1]
+    last = np.ones(len(w), dtype=bool)
+    last[:-1] = w[1:] != w[:-1]
+    prev = np.empty(len(w), dtype=np.int64)
+    prev[1:] = order[:-1]
+    # the first occurrence of each wire points to the last occurrence of the same wire
+    group_last = order[last]                       # one entry per wire group, in group order
+    group_id = np.cumsum(first) - 1
+    prev[first] = group_last[group_id[first]]
+    perm = np.empty(len(w), dtype=np.int64)
+    perm[order] = prev
+    return perm
+
+
+@dataclass
+class Proof:
+    """plonk.Proof of gnark v0.8.0 (bn254): points as 64-byte G1Affine images, scalars as 32-byte fr images."""
+    blob: bytes  # 832 bytes, layout documented at b200zk_plonk_prove
+
+    def points(self) -> List[bytes]:
+        return [self.blob[64 * i: 64 * i + 64] for i in range(9)]
+
+    def scalars(self) -> List[int]:
+        return fr_from_mont(self.blob[576:])
+
+    @staticmethod
+    def _compress(pt: bytes) -> bytes:
+        x = int.from_bytes(pt[:32], "little") * _R_INV_P % P_MOD
+        y = int.from_bytes(pt[32:], "little") * _R_INV_P % P_MOD
+        if pt == b"\0" * 64:
+            return b"\x40" + b"\0" * 31
+        b = bytearray(x.to_bytes(32, "big"))
+        b[0] |= 0x80 if y <= (P_MOD - 1) // 2 else 0xC0
+        return bytes(b)
+
+    def to_gnark_bytes(self) -> bytes:
+        """proof.WriteTo: LRO[3], Z, H[3] compressed | BatchedProof.H | u32 7 | 7 fr | ZShifted.H | fr  (548 B)."""
+        p = self.points()
+        s = self.scalars()
+        out = b"".join(self._compress(x) for x in p[:7]) + self._compress(p[7])
+        out += (7).to_bytes(4, "big") + b"".join(v.to_bytes(32, "big") for v in s[:7])
+        out += self._compress(p[8]) + s[7].to_bytes(32, "big")
+        return out
+
+
+class ProvingKey:
+    """plonk.ProvingKey resident on the device (selectors, permutation polynomials, their Lagrange-coset forms, SRS)."""
+
+    def __init__(self):
+        self.handle = None
+
+    @classmethod
+    def Setup(cls, cs: SparseR1CS, srs: SRS, ctx: Optional[Context] = None) -> "ProvingKey":
+        """plonk.Setup(spr, srs): rows = [placeholders | constraints | padding]."""
+        self = cls()
+        self.ctx = ctx or srs.ctx
+        self.srs = srs
+        size_system = cs.nb_constraints + cs.nb_public
+        self.log2n = max(_next_pow2_log(size_system), 1)
+        n = 1 << self.log2n
+        self.log2n_big = _next_pow2_log((8 if size_system < 6 else 4) * size_system)
+        self.log2n_big = max(self.log2n_big, self.log2n + 2)
+        self.n = n
+        self.nb_public = cs.nb_public
+        self.nb_wires = max(cs.nb_public + cs.nb_secret, 1)
+        off = cs.nb_public
+
+        def column(vals, placeholder):
+            col = [placeholder] * off + list(vals) + [0] * (n - off - len(vals))
+            return np.ascontiguousarray(fr_to_mont(col))
+
+        ql = column(cs.ql, R_MOD - 1)
+        qr, qm, qo, qk = (column(v, 0) for v in (cs.qr, cs.qm, cs.qo, cs.qk))
+        lro = np.zeros(3 * n, dtype=np.uint32)
+        lro[:off] = np.arange(off, dtype=np.uint32)
+        k = cs.nb_constraints
+        lro[off:off + k] = np.asarray(cs.a, dtype=np.uint32)
+        lro[n + off:n + off + k] = np.asarray(cs.b, dtype=np.uint32)
+        lro[2 * n + off:2 * n + off + k] = np.asarray(cs.c, dtype=np.uint32)
+        perm = build_permutation(lro)
+        self.lro, self.permutation = lro, perm
+        return self._finish(ql, qr, qm, qo, qk, perm, lro)
+
+    @classmethod
+    def SetupRaw(cls, srs: SRS, log2n: int, log2n_big: int, nb_public: int, nb_wires: int, ql, qr, qm, qo, qk,
+                 lro: np.ndarray, ctx: Optional[Context] = None) -> "ProvingKey":
+        """Setup from ready-made Lagrange columns (n*32-byte Montgomery images) — for large synthetic circuits."""
+        self = cls()
+        self.ctx = ctx or srs.ctx
+        self.srs = srs
+        self.log2n, self.log2n_big, self.n = log2n, log2n_big, 1 << log2n
+        self.nb_public, self.nb_wires = nb_public, nb_wires
+        perm = build_permutation(lro)
+        self.lro, self.permutation = lro, perm
+        return self._finish(*(np.ascontiguousarray(x) for x in (ql, qr, qm, qo, qk)), perm, lro)
+
+    def _finish(self, ql, qr, qm, qo, qk, perm, lro) -> "ProvingKey":
+        lib, h = self.ctx.lib, self.ctx.handle
+        out = C.c_void_p()
+        perm = np.ascontiguousarray(perm, dtype=np.int64)
+        lro = np.ascontiguousarray(lro, dtype=np.uint32)
+        rc = lib.b200zk_plonk_setup(h, self.srs.handle, self.log2n, self.log2n_big, self.nb_public, self.nb_wires,
+                                    ql.ctypes.data, qr.ctypes.data, qm.ctypes.data, qo.ctypes.data, qk.ctypes.data,
+                                    perm.ctypes.data, lro.ctypes.data, C.byref(out))
+        _lib.check(h, rc)
+        self.handle = out
+        vk = np.zeros(8 * 64, dtype=np.uint8)
+        _lib.check(h, lib.b200zk_plonk_vk(h, self.handle, vk.ctypes.data))
+        self.vk_points = [vk[64 * i: 64 * i + 64].tobytes() for i in range(8)]  # S0,S1,S2,Ql,Qr,Qm,Qo,Qk
+        return self
+
+    def poly(self, which: int) -> bytes:
+        """Ql,Qr,Qm,Qo,CQk (canonical), LQk (Lagrange), S1,S2,S3 (canonical) — for ProvingKey.WriteTo."""
+        out = np.zeros(self.n * 32, dtype=np.uint8)
+        _lib.check(self.ctx.handle, self.ctx.lib.b200zk_plonk_pk_poly(self.ctx.handle, self.handle, which, out.ctypes.data))
+        return out.tobytes()
+
+    def Prove(self, solution, blinding) -> Proof:
+        """plonk.Prove: solution = every wire's value (public wires first), blinding = 9 fr.SetRandom draws
+        (Montgomery images, order L,L,R,R,O,O,Z,Z,Z)."""
+        sol = np.ascontiguousarray(np.frombuffer(bytes(solution), dtype=np.uint8) if not isinstance(solution, np.ndarray) else solution)
+        bl = np.ascontiguousarray(np.frombuffer(bytes(blinding), dtype=np.uint8) if not isinstance(blinding, np.ndarray) else blinding)
+        assert sol.nbytes == self.nb_wires * 32 and bl.nbytes == 9 * 32
+        out = np.zeros(832, dtype=np.uint8)
+        rc = self.ctx.lib.b200zk_plonk_prove(self.ctx.handle, self.handle, sol.ctypes.data, bl.ctypes.data, out.ctypes.data)
+        _lib.check(self.ctx.handle, rc)
+        return Proof(out.tobytes())
+
+    def close(self) -> None:
+        if self.handle and self.ctx.handle:
+            self.ctx.lib.b200zk_plonk_pk_free(self.ctx.handle, self.handle)
+        self.handle = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass

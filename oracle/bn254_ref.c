@@ -628,3 +628,29 @@ void oracle_random_fr(void* out, size_t n, uint64_t seed) {
     if (!fe_geq(v.l, FR.m)) o[i++] = v;
   }
 }
+
+/* out[i] = scalars[i] * G (G = (1,2)), scalars Montgomery fr; affine outputs; parallel over nthreads.
+ * Used to build kzg.NewSRS-style bases for the PLONK oracle ([alpha^i]G). */
+typedef struct { const fe* sc; g1a* out; } mulgen_arg;
+static void mulgen_range(void* p, size_t lo, size_t hi, int tid) {
+  (void)tid;
+  mulgen_arg* m = (mulgen_arg*)p;
+  g1a G;
+  G.x = FP.one;
+  fe_add(&FP, &G.y, &FP.one, &FP.one);
+  for (size_t i = lo; i < hi; i++) {
+    fe s;
+    fe_from_mont(&FR, &s, &m->sc[i]);
+    g1x acc;
+    g1x_set_inf(&acc);
+    for (int b = 255; b >= 0; b--) {
+      g1x_double(&acc);
+      if ((s.l[b / 64] >> (b % 64)) & 1) g1x_add_mixed(&acc, &G, 0);
+    }
+    g1x_to_affine(&m->out[i], &acc);
+  }
+}
+void oracle_g1_mul_gen_batch(const void* scalars, size_t n, void* out, int nthreads) {
+  mulgen_arg m = {(const fe*)scalars, (g1a*)out};
+  parallel_for(n, nthreads < 1 ? 1 : nthreads, mulgen_range, &m);
+}

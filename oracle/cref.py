@@ -38,6 +38,7 @@ def load() -> C.CDLL:
         lib.oracle_g1_arith_progression.argtypes = [vp, vp, sz, vp]
         lib.oracle_g1_add_affine.argtypes = [vp, vp, vp]
         lib.oracle_random_fr.argtypes = [vp, sz, C.c_uint64]
+        lib.oracle_g1_mul_gen_batch.argtypes = [vp, sz, vp, i]
         for name in ("oracle_fr_mul", "oracle_fp_mul", "oracle_fr_add", "oracle_fr_sub"):
             getattr(lib, name).argtypes = [vp, vp, vp]
         for name in ("oracle_fr_inv", "oracle_fp_inv"):
@@ -104,4 +105,14 @@ def g1_arith_progression(first_affine: bytes, step_affine: bytes, n: int) -> np.
     out = np.zeros(n * 64, dtype=np.uint8)
     rc = load().oracle_g1_arith_progression(f.ctypes.data, s.ctypes.data, n, out.ctypes.data)
     assert rc == 0
+    return out
+
+
+def g1_mul_gen_batch(scalars_mont, n: int | None = None, nthreads: int | None = None) -> np.ndarray:
+    """[s_i * G] for Montgomery-form scalars; (n*64,) uint8."""
+    s = _buf(scalars_mont)
+    if n is None:
+        n = s.nbytes // 32
+    out = np.zeros(n * 64, dtype=np.uint8)
+    load().oracle_g1_mul_gen_batch(s.ctypes.data, n, out.ctypes.data, nthreads or ncores())
     return out

@@ -1,0 +1,95 @@
+"""GPU parity of the device-resident PLONK prover: for the same SRS, circuit, witness and blinding stream the CUDA
+prover must reproduce the oracle's verifying key and proof BYTE FOR BYTE (gnark proof.WriteTo layout), and every
+proof must pass the independent verifier (pairing check)."""
+import numpy as np
+import pytest
+
+import noir_backend_using_gnark_b200 as zk
+from noir_backend_using_gnark_b200 import plonk as zkp
+from oracle import bn254 as o
+from oracle import plonk as pl
+from tests.test_plonk_oracle import FIXTURES
+
+pytestmark = pytest.mark.gpu
+ALPHA = o.random_fr(1, 0xB2000005)[0]
+
+
+def blinding_bytes(seed: int) -> np.ndarray:
+    st = pl.BlindingStream(seed)
+    return np.frombuffer(b"".join(o.limbs_le(st.next_mont()) for _ in range(9)), dtype=np.uint8)
+
+
+def to_product_cs(cs: pl.SparseR1CS) -> zkp.SparseR1CS:
+    g = cs.gates
+    return zkp.SparseR1CS(cs.nb_public, cs.nb_secret, [x.ql for x in g], [x.qr for x in g], [x.qm for x in g],
+                          [x.qo for x in g], [x.qk for x in g], [x.a for x in g], [x.b for x in g], [x.c for x in g])
+
+
+def check_against_oracle(ctx, cs_o: pl.SparseR1CS, witness, srs_size: int, seed: int):
+    srs_o = pl.SRS(srs_size, ALPHA)
+    srs_d = zk.SRS.NewSRS(srs_size, o.fr_to_mont_bytes([ALPHA]), ctx)
+    assert srs_d.download() == srs_o.g1_bytes.tobytes()
+    pk_o = pl.setup(cs_o, srs_o)
+    pk_d = zkp.ProvingKey.Setup(to_product_cs(cs_o), srs_d, ctx)
+    assert (pk_d.log2n, pk_d.log2n_big) == (pk_o.n.bit_length() - 1, pk_o.n_big.bit_length() - 1)
+    assert pk_d.permutation.tolist() == pk_o.permutation
+    vk = pk_o.vk
+    want_vk = [o.g1_to_bytes([p]) for p in vk.S + [vk.Ql, vk.Qr, vk.Qm, vk.Qo, vk.Qk]]
+    assert pk_d.vk_points == want_vk
+    assert pk_d.poly(6) == o.fr_to_mont_bytes(pk_o.s1)
+    proof_o = pl.prove(cs_o, pk_o, srs_o, witness, pl.BlindingStream(seed))
+    proof_d = pk_d.Prove(o.fr_to_mont_bytes(witness), blinding_bytes(seed))
+    assert proof_d.to_gnark_bytes() == proof_o.to_bytes()
+    assert pl.verify(pl.Proof.from_bytes(proof_d.to_gnark_bytes()), vk, witness[: cs_o.nb_public], srs_o.g2)
+    pk_d.close()
+    srs_d.close()
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2])
+def test_reference_fixture_circuits(ctx, idx):
+    """config 1: the ACIR circuits embedded in the reference's main() through the real decode path."""
+    js, vals = FIXTURES[idx]
+    vals = [v % o.R_MOD for v in vals]
+    cs_o, pub, sec = pl.build_sparse_r1cs(pl.decode_acir(js), vals)
+    check_against_oracle(ctx, cs_o, pub + sec, 128, 0xB2000006 + idx)
+
+
+@pytest.mark.parametrize("gates,nb_public", [(1, 1), (5, 1), (13, 1), (200, 3), (1023, 1), (5000, 2)])
+def test_synthetic_chain_byte_identical(ctx, gates, nb_public):
+    cs_o, x = pl.synthetic_chain_circuit(gates, 0xB2000004 + gates, nb_public)
+    size = 1
+    while size < gates + nb_public:
+        size <<= 1
+    check_against_oracle(ctx, cs_o, x, size + 3, 0xB2000006)
+
+
+def test_different_blinding_changes_proof_but_verifies(ctx):
+    cs_o, x = pl.synthetic_chain_circuit(50, 3)
+    srs_o = pl.SRS(67, ALPHA)
+    srs_d = zk.SRS.NewSRS(67, o.fr_to_mont_bytes([ALPHA]), ctx)
+    pk_o = pl.setup(cs_o, srs_o)
+    pk_d = zkp.ProvingKey.Setup(to_product_cs(cs_o), srs_d, ctx)
+    p1 = pk_d.Prove(o.fr_to_mont_bytes(x), blinding_bytes(1)).to_gnark_bytes()
+    p2 = pk_d.Prove(o.fr_to_mont_bytes(x), blinding_bytes(2)).to_gnark_bytes()
+    assert p1 != p2
+    for p in (p1, p2):
+        assert pl.verify(pl.Proof.from_bytes(p), pk_o.vk, x[:1], srs_o.g2)
+    pk_d.close()
+    srs_d.close()
+
+
+def test_large_circuit_verifies(ctx):
+    """2^18 rows: the oracle prover is too slow here, the O(1) verifier is not — the proof must verify."""
+    gates = (1 << 18) - 1
+    cs_o, x = pl.synthetic_chain_circuit(gates, 0xB2000004)
+    n = 1 << 18
+    srs_d = zk.SRS.NewSRS(n + 3, o.fr_to_mont_bytes([ALPHA]), ctx)
+    pk_d = zkp.ProvingKey.Setup(to_product_cs(cs_o), srs_d, ctx)
+    proof = pk_d.Prove(o.fr_to_mont_bytes(x), blinding_bytes(9))
+    S = [o.g1_from_bytes(b)[0] for b in pk_d.vk_points]
+    dom = o.Domain(n)
+    vk = pl.VerifyingKey(n, pow(n, -1, o.R_MOD), dom.generator, 1, 5, S[:3], S[3], S[4], S[5], S[6], S[7])
+    g2 = (pl.G2_GEN, pl.g2_mul(pl.G2_GEN, ALPHA))
+    assert pl.verify(pl.Proof.from_bytes(proof.to_gnark_bytes()), vk, x[:1], g2)
+    pk_d.close()
+    srs_d.close()
