@@ -43,6 +43,17 @@ def env_int(name: str, default: int) -> int:
         return default
 
 
+def random_fr_images(n: int, seed: int):
+    """n uniform-ish fr elements as in-memory (Montgomery) images: 4 x u64 limbs, top limb < 2^60 (< r).
+    Input synthesis for the B200 arm — deliberately NOT the oracle's generator."""
+    import numpy as np
+
+    rng = np.random.default_rng(seed)
+    limbs = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64) * 2 + rng.integers(0, 2, size=(n, 4), dtype=np.uint64)
+    limbs[:, 3] &= (1 << 60) - 1
+    return limbs.view(np.uint8).reshape(-1)
+
+
 def load_peaks() -> dict:
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -178,14 +189,56 @@ def run_reference(args, rank: int, world: int) -> None:
 # ------------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------------
+def run_prove(ctx, log2n: int) -> dict:
+    """BASELINE metric 1: full PLONK prove latency (device-resident prover, b200zk_plonk_prove) on the synthetic
+    chain circuit of 2^log2n - 1 gates + 1 public input; the proof is checked by the independent verifier."""
+    import numpy as np
+
+    import noir_backend_using_gnark_b200 as zk
+    from noir_backend_using_gnark_b200 import plonk as zkp
+
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    from prove_bench import synthetic
+
+    n = 1 << log2n
+    c = synthetic(log2n)
+    a_int = SEED_SRS * 0x9E3779B97F4A7C15 % zkp.R_MOD
+    srs = zk.SRS.NewSRS(n + 3, zkp.fr_to_mont([a_int]), ctx)
+    t0 = time.perf_counter()
+    pk = zkp.ProvingKey.SetupRaw(srs, log2n, log2n + 2, 1, c["nb_wires"], c["ql"], c["qr"], c["qm"], c["qo"], c["qk"],
+                                 c["lro"], ctx)
+    setup_ms = (time.perf_counter() - t0) * 1e3
+    blind = random_fr_images(9, 0xB2000006)
+    pk.Prove(c["sol"], blind)  # warm-up
+    times = []
+    l0 = ctx.launch_count
+    for _ in range(3):
+        t0 = time.perf_counter()
+        proof = pk.Prove(c["sol"], blind)
+        times.append((time.perf_counter() - t0) * 1e3)
+    launches = (ctx.launch_count - l0) // 3
+    # acceptance by the independent verifier (checker only: oracle/plonk.py pairing check)
+    from oracle import bn254 as o
+    from oracle import plonk as pl
+
+    S = [o.g1_from_bytes(b)[0] for b in pk.vk_points]
+    vk = pl.VerifyingKey(n, pow(n, -1, zkp.R_MOD), o.Domain(n).generator, 1, 5, S[:3], S[3], S[4], S[5], S[6], S[7])
+    ok = bool(pl.verify(pl.Proof.from_bytes(proof.to_gnark_bytes()), vk, [c["x0"]], (pl.G2_GEN, pl.g2_mul(pl.G2_GEN, a_int))))
+    pk.close()
+    srs.close()
+    return {"metric": "plonk_prove_latency", "log2_gates": log2n, "ms": min(times), "ms_all": times, "unit": "ms",
+            "higher_is_better": False, "setup_ms": setup_ms, "launches_per_prove": int(launches), "verified": ok,
+            "api": "b200zk_plonk_prove (host solution vector in, 832-byte proof out; H2D/D2H included)",
+            "h2d_bytes": n * 32 + 288, "d2h_bytes": 832}
+
+
 def run_b200(args, rank: int, world: int, local_rank: int) -> None:
     import numpy as np
     import torch
     import torch.distributed as dist
 
     import noir_backend_using_gnark_b200 as zk
-    from oracle import bn254 as o      # input synthesis + cpu_baseline leg only
-    from oracle import cref
+    from noir_backend_using_gnark_b200 import plonk as zkp
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -197,9 +250,9 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
 
     log2n = args.log2n
     n = 1 << log2n
-    alpha = o.random_fr(1, SEED_SRS)[0]
-    srs = zk.SRS.NewSRS(n, o.fr_to_mont_bytes([alpha]), ctx, first=rank * n)
-    h_sc = torch.from_numpy(cref.random_fr(n, SEED_SCALARS + rank)).pin_memory()
+    alpha_img = zkp.fr_to_mont([SEED_SRS * 0x9E3779B97F4A7C15 % zkp.R_MOD])
+    srs = zk.SRS.NewSRS(n, alpha_img, ctx, first=rank * n)
+    h_sc = torch.from_numpy(random_fr_images(n, SEED_SCALARS + rank)).pin_memory()
     d_sc = h_sc.to(dev)
     torch.cuda.synchronize()
 
@@ -293,7 +346,7 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
     ntt_info = None
     if not args.no_ntt:
         nlog = args.ntt_log2n
-        a = torch.from_numpy(cref.random_fr(1 << nlog, SEED_NTT)).to(dev)
+        a = torch.from_numpy(random_fr_images(1 << nlog, SEED_NTT)).to(dev)
         torch.cuda.synchronize()
         d = zk.Domain(1 << nlog, ctx)
         for _ in range(3):
@@ -315,10 +368,14 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
                     "passes": -(-nlog // 8) if nlog > 10 else 1}
         del a
 
+    prove_info = None
+    if not args.no_prove:
+        prove_info = run_prove(ctx, args.prove_log2n)
+
     cpu = None
     if not args.no_cpu:
         ns = 1 << min(CPU_SAMPLE_LOG2, log2n)
-        pts = np.frombuffer(srs.download(0, ns), dtype=np.uint8)
+        pts = np.frombuffer(srs.download(0, ns), dtype=np.uint8)  # cpu_baseline leg: the only oracle use in this arm
         dt, cores = cpu_msm_sample(pts, h_sc.numpy()[: ns * 32], ns, reps=1)
         cpu = {"value": ns / dt / 1e6, "unit": "Mpoints/s", "cores": cores, "kind": "port",
                "sample": "first 2^%d points of the same MSM, C restatement of gnark-crypto MultiExp on all host cores "
@@ -355,6 +412,7 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
                      "hbm_bytes_algorithmic": 96 * n},
         "phase_share": phase_share,
         "ntt": ntt_info,
+        "plonk_prove": prove_info,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
@@ -373,6 +431,8 @@ def main() -> None:
     ap.add_argument("--ntt-log2n", type=int, default=24)
     ap.add_argument("--no-ntt", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-prove", action="store_true")
+    ap.add_argument("--prove-log2n", type=int, default=22)
     args = ap.parse_args()
     rank = env_int("RANK", 0)
     world = env_int("WORLD_SIZE", 1)
