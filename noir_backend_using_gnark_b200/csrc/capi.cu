@@ -194,7 +194,20 @@ void b200zk_bases_free(b200zk_ctx* ctx, b200zk_bases* bases) {
     }
     cudaFree(const_cast<void*>(bases->dev));
   }
+  if (bases->table) {
+    if (ctx) {
+      cudaSetDevice(ctx->device);
+      cudaStreamSynchronize(ctx->stream);
+    }
+    cudaFree(bases->table);
+  }
   delete bases;
+}
+
+int b200zk_bases_precompute(b200zk_ctx* ctx, b200zk_bases* bases, int c) {
+  B200ZK_TRY(enter(ctx));
+  if (!bases || (c != 0 && (c < 10 || c > 23))) return B200ZK_ERR_BAD_ARG;
+  return msm_precompute_run(ctx, bases, c);
 }
 
 size_t b200zk_bases_len(const b200zk_bases* bases) { return bases ? bases->n : 0; }

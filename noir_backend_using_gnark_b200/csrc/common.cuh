@@ -44,6 +44,9 @@ struct b200zk_bases {
   const void* dev = nullptr;  // n x 64 B affine points
   size_t n = 0;
   bool owned = false;
+  // optional window table (b200zk_bases_precompute): table[j*n + i] = 2^(tab_c*j) * P_i, j < tab_W; row 0 = the bases
+  void* table = nullptr;
+  unsigned tab_c = 0, tab_W = 0;
 };
 
 struct b200zk_ctx {
@@ -144,6 +147,7 @@ int bit_reverse_run(b200zk_ctx* ctx, void* a_dev, unsigned log2n);
 void ntt_free_domains(b200zk_ctx* ctx);
 int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const void* scalars_dev, size_t n,
             void* out_dev, int out_kind);
+int msm_precompute_run(b200zk_ctx* ctx, b200zk_bases* bases, int c);
 int g1_sum_run(b200zk_ctx* ctx, const void* partials_dev, size_t count, void* out_affine_dev);
 int microbench_run(b200zk_ctx* ctx, int which, double* out_ops_per_s);
 int srs_generate_run(b200zk_ctx* ctx, const void* alpha_dev, size_t first, size_t n, void* out_dev);

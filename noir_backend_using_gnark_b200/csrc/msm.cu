@@ -2,16 +2,21 @@
 // ((*G1Affine).MultiExp: partitionScalars + processChunkG1* + msmReduceChunkG1Affine), reached in the reference
 // through kzg.Commit inside plonk.Prove / plonk.Setup (/root/reference/gnark_backend_ffi/backend/plonk/plonk.go:67, :21).
 //
+// Pippenger with signed c-bit digits.  Two modes:
+//   classic      W = ceil(255/c) windows, 2^(c-1) buckets per window, window sums combined by Horner (c doublings each)
+//   precomputed  the bases are static (the KZG SRS), so b200zk_bases_precompute stores 2^(c*j) * P_i for every window j
+//                once; every (point, window) pair then lands in ONE shared set of 2^(c-1) buckets, which removes the
+//                per-window reduction and the Horner tail and lets c grow to ~log2(n)-2 (fewer additions per point)
 // Pipeline (all on the context stream, no host synchronisation):
-//   1 msm_digits_kernel     scalar: Montgomery -> regular, signed c-bit digits (2^(c-1) buckets per window),
-//                           digit matrix [window][point] + bucket histogram (global atomics)
-//   2 exclusive scan         bucket start offsets
-//   3 msm_scatter_kernel    counting sort: (point index | sign) grouped by (window, bucket)
-//   4 msm_accumulate_kernel one thread per bucket walks its run: extended-Jacobian mixed additions, next point
-//                           prefetched while the current addition runs; over-long runs (skewed scalars) are left to
-//   4b msm_big_* kernels    which split a run over many CTAs and tree-reduce the partial sums
-//   5 msm_reduce_l1/l2      per-window sum_b b*B[b] by three levels of 32-wide running sums
-//   6 msm_final_kernel      Horner over windows (c doublings each), then canonical affine (or XYZZ partial)
+//   1 msm_hist_kernel        scalar: Montgomery -> regular, signed digits, bucket histogram (global atomics)
+//   2 exclusive scan          bucket start offsets (CUB)
+//   3 msm_scatter_kernel     counting sort: (table index | sign) grouped by bucket
+//   4 msm_accumulate_kernel  one thread per bucket walks its run: 64-byte affine gathers (next point prefetched),
+//                            extended-Jacobian mixed additions; over-long runs (skewed scalars) are left to
+//   4b msm_big_* kernels     which split a run over many CTAs and tree-reduce the partial sums in shared memory
+//   5 msm_reduce_*           sum_b b*B[b]: running sums over 32-bucket chunks, then the chunk weights are split in
+//                            bit planes which are summed in parallel (warp-shuffle trees) and recombined by doublings
+//   6 msm_final_kernel       Horner over windows (classic mode only), canonical affine (or XYZZ partial) output
 // The result is a canonical affine point, so it is bit-identical to gnark's for any window size / summation order.
 #include <cub/device/device_scan.cuh>
 #include "common.cuh"
@@ -19,25 +24,28 @@
 
 namespace b200zk {
 
-static constexpr int CHUNK = 32;          // buckets per running-sum chunk
-static constexpr int BIG_CHUNK = 8192;    // sorted entries per CTA in the long-run path
+static constexpr int CHUNK_LOG = 5;
+static constexpr int CHUNK = 1 << CHUNK_LOG;   // buckets per running-sum chunk
+static constexpr int BIG_CHUNK = 8192;         // sorted entries per CTA in the long-run path
 static constexpr int BIG_THREADS = 256;
+static constexpr int MAX_WINDOWS = 64;
+static constexpr int SLICE = 1024;             // chunk results per CTA in the bit-plane sums
+static constexpr int MAX_PLANES = 24;
 
 struct MsmShape {
-  unsigned c;         // window bits
-  unsigned W;         // number of windows
-  unsigned B;         // buckets per window = 2^(c-1)
-  unsigned big_len;   // runs longer than this go to the cooperative path
+  unsigned c;           // window bits
+  unsigned W;           // number of windows
+  unsigned B;           // buckets per bucket set = 2^(c-1)
+  unsigned nsets;       // bucket sets: W (classic) or 1 (precomputed)
+  unsigned key_stride;  // bucket id = w * key_stride + |digit| - 1     (B or 0)
+  unsigned tab_stride;  // table index = w * tab_stride + point index   (0 or table row length)
+  unsigned first;       // index of the first base used
+  unsigned big_len;     // runs longer than this go to the cooperative path
 };
 
-// ---------------------------------------------------------------------------------------------------
-// 1. digits + histogram
-// ---------------------------------------------------------------------------------------------------
-__global__ void msm_digits_kernel(const uint4* __restrict__ scalars, size_t n, MsmShape sh, int16_t* __restrict__ digits,
-                                  unsigned* __restrict__ counts) {
-  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  Fr s = fe_from_mont(fe_load<FrParams>(scalars + 2 * i));
+// signed-digit recoding of one scalar; calls f(w, digit) for every window (digit in [-B, B-1])
+template <class F>
+__device__ __forceinline__ void for_each_digit(const Fr& s, const MsmShape& sh, F f) {
   unsigned carry = 0;
   const unsigned mask = (1u << sh.c) - 1u;
   for (unsigned w = 0; w < sh.W; w++) {
@@ -45,7 +53,6 @@ __global__ void msm_digits_kernel(const uint4* __restrict__ scalars, size_t n, M
     const unsigned limb = bit >> 5, off = bit & 31;
     unsigned v = 0;
     if (limb < 8) {
-      // 64-bit window over two limbs
       unsigned lo = s.l[limb];
       unsigned hi = limb + 1 < 8 ? s.l[limb + 1] : 0u;
       v = (unsigned)((((uint64_t)hi << 32) | lo) >> off) & mask;
@@ -56,27 +63,43 @@ __global__ void msm_digits_kernel(const uint4* __restrict__ scalars, size_t n, M
       d -= (int)(2 * sh.B);
       carry = 1;
     }
-    digits[(size_t)w * n + i] = (int16_t)d;
-    if (d != 0) {
-      unsigned mag = d < 0 ? (unsigned)(-d) : (unsigned)d;
-      atomicAdd(&counts[w * sh.B + (mag - 1)], 1u);
-    }
+    f(w, d);
   }
 }
 
+__device__ __forceinline__ Fr load_scalar_regular(const uint4* __restrict__ scalars, size_t i) {
+  // the limbs are indexed dynamically by for_each_digit: keep them addressable
+  return fe_from_mont(fe_load<FrParams>(scalars + 2 * i));
+}
+
 // ---------------------------------------------------------------------------------------------------
-// 3. scatter (counting sort)
+// 1. histogram, 3. scatter
 // ---------------------------------------------------------------------------------------------------
-__global__ void msm_scatter_kernel(const int16_t* __restrict__ digits, size_t n, MsmShape sh, unsigned* __restrict__ cursor,
-                                   unsigned* __restrict__ sorted) {
+__global__ void __launch_bounds__(256) msm_hist_kernel(const uint4* __restrict__ scalars, size_t n, MsmShape sh,
+                                                       unsigned* __restrict__ counts) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  unsigned w = blockIdx.y;
   if (i >= n) return;
-  int d = digits[(size_t)w * n + i];
-  if (d == 0) return;
-  unsigned mag = d < 0 ? (unsigned)(-d) : (unsigned)d;
-  unsigned pos = atomicAdd(&cursor[w * sh.B + (mag - 1)], 1u);
-  sorted[pos] = (unsigned)i | (d < 0 ? 0x80000000u : 0u);
+  Fr s = load_scalar_regular(scalars, i);
+  for_each_digit(s, sh, [&](unsigned w, int d) {
+    if (d != 0) {
+      unsigned mag = d < 0 ? (unsigned)(-d) : (unsigned)d;
+      atomicAdd(&counts[w * sh.key_stride + (mag - 1)], 1u);
+    }
+  });
+}
+
+__global__ void __launch_bounds__(256) msm_scatter_kernel(const uint4* __restrict__ scalars, size_t n, MsmShape sh,
+                                                          unsigned* __restrict__ cursor, unsigned* __restrict__ sorted) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr s = load_scalar_regular(scalars, i);
+  for_each_digit(s, sh, [&](unsigned w, int d) {
+    if (d != 0) {
+      unsigned mag = d < 0 ? (unsigned)(-d) : (unsigned)d;
+      unsigned pos = atomicAdd(&cursor[w * sh.key_stride + (mag - 1)], 1u);
+      sorted[pos] = (w * sh.tab_stride + sh.first + (unsigned)i) | (d < 0 ? 0x80000000u : 0u);
+    }
+  });
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -202,88 +225,111 @@ __global__ void __launch_bounds__(BIG_THREADS) msm_big_reduce_kernel(const unsig
 }
 
 // ---------------------------------------------------------------------------------------------------
-// 5. per-window bucket reduction: S_w = sum_{b=1..B} b * bucket[b-1]
-//    level 1: chunk t of 32 buckets -> run1 = sum, acc1 = sum_j (j+1)*item_j
-//    level 2: chunk u of 32 level-1 chunks -> asum = sum acc1, run2 = sum run1, acc2 = sum_j j*run1_j
-//    final  : S_w = sum_u asum_u + 32*(sum_u acc2_u + 32 * sum_u u*run2_u)
+// 5. bucket reduction per bucket set:  S = sum_{b=1..B} b * bucket[b-1]
+//    R1: chunk t (32 buckets):  run_t = sum_j X_{32t+j},  acc_t = sum_j (j+1) X_{32t+j}
+//        => S = sum_t acc_t + 32 * sum_t t * run_t
+//    R2: the weights t are split in bit planes: plane 0 sums acc_t, plane 1+k sums run_t over {t : bit k of t set};
+//        each CTA sums one slice of one plane (thread-serial partial sums, then a shared-memory tree)
+//    R3: one CTA per set: warp p finishes plane p (lane partial sums + warp-shuffle tree), then
+//        S = P_0 + 32 * sum_k 2^k P_{1+k}  by doublings
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) msm_reduce_l1_kernel(const void* __restrict__ buckets, unsigned nchunks_total,
-                                                            void* __restrict__ run1, void* __restrict__ acc1) {
+__global__ void __launch_bounds__(128) msm_reduce_r1_kernel(const void* __restrict__ buckets, unsigned nchunks_total,
+                                                            void* __restrict__ run, void* __restrict__ acc_out) {
   unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nchunks_total) return;
-  G1XYZZ run = g1_xyzz_inf(), acc = g1_xyzz_inf();
+  G1XYZZ r = g1_xyzz_inf(), a = g1_xyzz_inf();
   for (int j = CHUNK - 1; j >= 0; j--) {
     G1XYZZ q = g1_load_xyzz(buckets, (size_t)t * CHUNK + j);
-    g1_add(run, q);
-    g1_add(acc, run);
+    g1_add(r, q);
+    g1_add(a, r);
   }
-  g1_store_xyzz(run1, t, run);
-  g1_store_xyzz(acc1, t, acc);
+  g1_store_xyzz(run, t, r);
+  g1_store_xyzz(acc_out, t, a);
 }
 
-__global__ void __launch_bounds__(128) msm_reduce_l2_kernel(const void* __restrict__ run1, const void* __restrict__ acc1,
-                                                            unsigned n1_per_window, unsigned n2_per_window, unsigned W,
-                                                            void* __restrict__ asum, void* __restrict__ run2,
-                                                            void* __restrict__ acc2) {
-  unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
-  if (id >= n2_per_window * W) return;
-  unsigned w = id / n2_per_window, u = id % n2_per_window;
-  G1XYZZ a = g1_xyzz_inf(), run = g1_xyzz_inf(), acc = g1_xyzz_inf();
-  for (int j = CHUNK - 1; j >= 0; j--) {
-    unsigned t = u * CHUNK + j;
-    if (t >= n1_per_window) continue;
-    size_t idx = (size_t)w * n1_per_window + t;
-    G1XYZZ q = g1_load_xyzz(acc1, idx);
-    g1_add(a, q);
-    q = g1_load_xyzz(run1, idx);
-    g1_add(run, q);
-    if (j > 0) g1_add(acc, run);
-  }
-  g1_store_xyzz(asum, id, a);
-  g1_store_xyzz(run2, id, run);
-  g1_store_xyzz(acc2, id, acc);
-}
-
-// ---------------------------------------------------------------------------------------------------
-// 6. window sums + Horner + normalisation
-// ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64) msm_final_kernel(const void* __restrict__ asum, const void* __restrict__ run2,
-                                                       const void* __restrict__ acc2, unsigned n2_per_window, MsmShape sh,
-                                                       void* __restrict__ out, int out_kind) {
-  __shared__ G1XYZZ wsum[64];  // W <= 43 (c >= 6)
-  const unsigned w = threadIdx.x;
-  if (w < sh.W) {
-    G1XYZZ A = g1_xyzz_inf(), Bs = g1_xyzz_inf(), run = g1_xyzz_inf(), C = g1_xyzz_inf();
-    for (int u = (int)n2_per_window - 1; u >= 0; u--) {
-      size_t idx = (size_t)w * n2_per_window + u;
-      G1XYZZ q = g1_load_xyzz(asum, idx);
-      g1_add(A, q);
-      q = g1_load_xyzz(acc2, idx);
-      g1_add(Bs, q);
-      q = g1_load_xyzz(run2, idx);
-      g1_add(run, q);
-      if (u > 0) g1_add(C, run);
+// grid = (slices, planes, sets)
+__global__ void __launch_bounds__(BIG_THREADS) msm_reduce_r2_kernel(const void* __restrict__ run, const void* __restrict__ acc_in,
+                                                                    unsigned chunks_per_set, unsigned nslices,
+                                                                    void* __restrict__ partial) {
+  extern __shared__ uint4 big_smem[];
+  G1XYZZ* sh_pts = reinterpret_cast<G1XYZZ*>(big_smem);
+  const unsigned slice = blockIdx.x, plane = blockIdx.y, set = blockIdx.z;
+  const unsigned lo = slice * SLICE;
+  const unsigned hi = lo + SLICE < chunks_per_set ? lo + SLICE : chunks_per_set;
+  G1XYZZ acc = g1_xyzz_inf();
+  for (unsigned t = lo + threadIdx.x; t < hi; t += BIG_THREADS) {
+    const size_t idx = (size_t)set * chunks_per_set + t;
+    if (plane == 0) {
+      G1XYZZ q = g1_load_xyzz(acc_in, idx);
+      g1_add(acc, q);
+    } else if ((t >> (plane - 1)) & 1u) {
+      G1XYZZ q = g1_load_xyzz(run, idx);
+      g1_add(acc, q);
     }
-    // S = A + 32*(Bs + 32*C)
-    for (int k = 0; k < 5; k++) g1_double(C);
-    g1_add(C, Bs);
-    for (int k = 0; k < 5; k++) g1_double(C);
-    g1_add(C, A);
-    wsum[w] = C;
   }
+  block_reduce_xyzz(acc, sh_pts);
+  if (threadIdx.x == 0) g1_store_xyzz(partial, ((size_t)set * gridDim.y + plane) * nslices + slice, acc);
+}
+
+__device__ __forceinline__ G1XYZZ warp_sum_xyzz(G1XYZZ v) {
+  // butterfly reduction with warp shuffles: every 32-bit limb of the point travels by __shfl_xor_sync
+  for (int d = 16; d > 0; d >>= 1) {
+    G1XYZZ o;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      o.x.l[i] = __shfl_xor_sync(0xffffffffu, v.x.l[i], d);
+      o.y.l[i] = __shfl_xor_sync(0xffffffffu, v.y.l[i], d);
+      o.zz.l[i] = __shfl_xor_sync(0xffffffffu, v.zz.l[i], d);
+      o.zzz.l[i] = __shfl_xor_sync(0xffffffffu, v.zzz.l[i], d);
+    }
+    // both partners compute the same group element (the XYZZ representative may differ between partners,
+    // which is fine: only lane 0's value is used)
+    g1_add(v, o);
+  }
+  return v;
+}
+
+// grid = sets, block = 32 * nplanes threads
+__global__ void msm_reduce_r3_kernel(const void* __restrict__ partial, unsigned nplanes, unsigned nslices,
+                                     void* __restrict__ set_sums) {
+  __shared__ G1XYZZ plane_sum[MAX_PLANES];
+  const unsigned set = blockIdx.x, plane = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  G1XYZZ acc = g1_xyzz_inf();
+  for (unsigned s = lane; s < nslices; s += 32) {
+    G1XYZZ q = g1_load_xyzz(partial, ((size_t)set * nplanes + plane) * nslices + s);
+    g1_add(acc, q);
+  }
+  acc = warp_sum_xyzz(acc);
+  if (lane == 0) plane_sum[plane] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {
-    G1XYZZ total = wsum[sh.W - 1];
-    for (int ww = (int)sh.W - 2; ww >= 0; ww--) {
-      for (unsigned k = 0; k < sh.c; k++) g1_double(total);
-      g1_add(total, wsum[ww]);
+    G1XYZZ s = g1_xyzz_inf();
+    for (int k = (int)nplanes - 1; k >= 1; k--) {  // sum_k 2^(k-1) P_k
+      g1_double(s);
+      g1_add(s, plane_sum[k]);
     }
-    if (out_kind == 0) {
-      G1Affine r = g1_to_affine(total);
-      g1_store_affine(out, 0, r);
-    } else {
-      g1_store_xyzz(out, 0, total);
-    }
+    for (int k = 0; k < CHUNK_LOG; k++) g1_double(s);
+    g1_add(s, plane_sum[0]);
+    g1_store_xyzz(set_sums, set, s);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 6. window Horner (classic mode) + normalisation
+// ---------------------------------------------------------------------------------------------------
+__global__ void msm_final_kernel(const void* __restrict__ set_sums, MsmShape sh, void* __restrict__ out, int out_kind) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  G1XYZZ total = g1_load_xyzz(set_sums, sh.nsets - 1);
+  for (int w = (int)sh.nsets - 2; w >= 0; w--) {
+    for (unsigned k = 0; k < sh.c; k++) g1_double(total);
+    G1XYZZ q = g1_load_xyzz(set_sums, w);
+    g1_add(total, q);
+  }
+  if (out_kind == 0) {
+    G1Affine r = g1_to_affine(total);
+    g1_store_affine(out, 0, r);
+  } else {
+    g1_store_xyzz(out, 0, total);
   }
 }
 
@@ -304,12 +350,57 @@ __global__ void copy_u32_kernel(const unsigned* __restrict__ src, unsigned* __re
 }
 
 // ---------------------------------------------------------------------------------------------------
+// precomputation of window multiples: table[j*n + i] = 2^(c*j) * P_i  (affine), j < W; row 0 = the bases.
+// One thread per point: c doublings per window, the W-1 results normalised with ONE inversion (Montgomery's trick;
+// the per-window numerators and prefix products are parked in `tmp`).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) msm_precompute_kernel(const void* __restrict__ table, size_t n, size_t first,
+                                                             size_t count, unsigned c, unsigned W, void* __restrict__ tmp,
+                                                             void* __restrict__ table_out) {
+  size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  const size_t i = first + t;
+  G1Affine p = g1_load_affine(table, i);
+  if (g1_is_inf(p)) {
+    for (unsigned j = 1; j < W; j++) g1_store_affine(table_out, j * n + i, p);
+    return;
+  }
+  G1XYZZ acc;
+  acc.x = p.x;
+  acc.y = p.y;
+  acc.zz = fe_one<FpParams>();
+  acc.zzz = fe_one<FpParams>();
+  Fp pre = fe_one<FpParams>();
+  for (unsigned j = 1; j < W; j++) {
+    for (unsigned k = 0; k < c; k++) g1_double(acc);
+    Fp zz3 = fe_mul(acc.zz, acc.zzz);
+    G1XYZZ q;
+    q.x = fe_mul(acc.x, acc.zzz);  // x = X/ZZ  = X*ZZZ / (ZZ*ZZZ)
+    q.y = fe_mul(acc.y, acc.zz);   // y = Y/ZZZ = Y*ZZ  / (ZZ*ZZZ)
+    q.zz = pre;                    // product of the earlier denominators
+    q.zzz = zz3;
+    g1_store_xyzz(tmp, (j - 1) * count + t, q);
+    pre = fe_mul(pre, zz3);
+  }
+  Fp inv = fe_inv(pre);  // 1 / (all denominators)
+  for (unsigned j = W - 1; j >= 1; j--) {
+    G1XYZZ q = g1_load_xyzz(tmp, (j - 1) * count + t);
+    Fp einv = fe_mul(inv, q.zz);  // 1 / denominator_j
+    G1Affine a;
+    a.x = fe_mul(q.x, einv);
+    a.y = fe_mul(q.y, einv);
+    g1_store_affine(table_out, j * n + i, a);
+    inv = fe_mul(inv, q.zzz);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // host driver
 // ---------------------------------------------------------------------------------------------------
 static unsigned choose_window(size_t n) {
   unsigned lg = 0;
   while (((size_t)1 << (lg + 1)) <= n) lg++;
-  // fewer, larger windows as n grows; at least 2^5 buckets so the 32-wide reduction levels are full
+  // fewer, larger windows as n grows; at least 2^5 buckets so the 32-wide reduction chunks are full
   if (lg >= 23) return 16;
   if (lg >= 21) return 15;
   if (lg >= 19) return 14;
@@ -319,6 +410,47 @@ static unsigned choose_window(size_t n) {
   if (lg >= 11) return 10;
   if (lg >= 9) return 9;
   return 8;
+}
+
+int msm_precompute_run(b200zk_ctx* ctx, b200zk_bases* bases, int c_req) {
+  if (!bases || !bases->dev) return B200ZK_ERR_BAD_ARG;
+  if (bases->table) return B200ZK_OK;
+  const size_t n = bases->n;
+  if (n < 1024) return B200ZK_OK;  // not worth it: the classic path is used
+  unsigned lg = 0;
+  while (((size_t)1 << (lg + 1)) <= n) lg++;
+  unsigned c = c_req ? (unsigned)c_req : lg - 2;
+  if (c < 10) c = 10;
+  if (c > 23) c = 23;
+  const unsigned W = (255 + c - 1) / c;
+  if ((size_t)W * n >= ((size_t)1 << 31)) return B200ZK_ERR_UNSUPPORTED;
+  void* table = nullptr;
+  cudaError_t e = cudaMalloc(&table, (size_t)W * n * 64);
+  if (e != cudaSuccess) return set_cuda_error(ctx, e, "cudaMalloc(window table)");
+  const size_t chunk = n < ((size_t)1 << 18) ? n : ((size_t)1 << 18);
+  void* tmp = nullptr;
+  e = cudaMalloc(&tmp, (size_t)(W - 1) * chunk * 128);
+  if (e != cudaSuccess) {
+    cudaFree(table);
+    return set_cuda_error(ctx, e, "cudaMalloc(window table scratch)");
+  }
+  e = cudaMemcpyAsync(table, bases->dev, n * 64, cudaMemcpyDeviceToDevice, ctx->stream);
+  for (size_t first = 0; first < n && e == cudaSuccess; first += chunk) {
+    const size_t count = first + chunk <= n ? chunk : n - first;
+    msm_precompute_kernel<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(table, n, first, count, c, W, tmp, table);
+    ctx->launches++;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(tmp);
+  if (e != cudaSuccess) {
+    cudaFree(table);
+    return set_cuda_error(ctx, e, "msm_precompute_kernel");
+  }
+  bases->table = table;
+  bases->tab_c = c;
+  bases->tab_W = W;
+  return B200ZK_OK;
 }
 
 int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const void* scalars_dev, size_t n,
@@ -333,49 +465,66 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
     return B200ZK_OK;
   }
   MsmShape sh;
-  sh.c = ctx->forced_window ? (unsigned)ctx->forced_window : choose_window(n);
-  if (sh.c < 6) sh.c = 6;
-  if (sh.c > 16) sh.c = 16;
-  sh.W = (255 + sh.c - 1) / sh.c;  // c*W >= 255: the top window never produces a carry
-  sh.B = 1u << (sh.c - 1);
+  const bool use_table = bases->table && !ctx->forced_window && n * 16 >= bases->n;
+  const void* base_ptr;
+  if (use_table) {
+    sh.c = bases->tab_c;
+    sh.W = bases->tab_W;
+    sh.B = 1u << (sh.c - 1);
+    sh.nsets = 1;
+    sh.key_stride = 0;
+    sh.tab_stride = (unsigned)bases->n;
+    base_ptr = bases->table;
+  } else {
+    sh.c = ctx->forced_window ? (unsigned)ctx->forced_window : choose_window(n);
+    if (sh.c < 6) sh.c = 6;
+    if (sh.c > 16) sh.c = 16;
+    sh.W = (255 + sh.c - 1) / sh.c;  // c*W >= 255: the top window never produces a carry
+    sh.B = 1u << (sh.c - 1);
+    sh.nsets = sh.W;
+    sh.key_stride = sh.B;
+    sh.tab_stride = 0;
+    base_ptr = bases->dev;
+  }
+  sh.first = (unsigned)first_base;
   const size_t total = n * sh.W;
-  if (total >= ((size_t)1 << 32)) return B200ZK_ERR_UNSUPPORTED;
-  const unsigned nbuckets = sh.W * sh.B;
+  if (total >= ((size_t)1 << 32) || sh.W > MAX_WINDOWS) return B200ZK_ERR_UNSUPPORTED;
+  const unsigned nbuckets = sh.nsets * sh.B;
   {
     size_t avg = total / nbuckets;
     size_t bl = 4 * avg + 256;
     sh.big_len = (unsigned)(bl > 0x7fffffff ? 0x7fffffff : bl);
   }
-  const unsigned n1 = sh.B / CHUNK;                  // level-1 chunks per window
-  const unsigned n2 = (n1 + CHUNK - 1) / CHUNK;      // level-2 chunks per window
+  const unsigned chunks_per_set = sh.B / CHUNK;
+  unsigned chunk_bits = 0;
+  while ((1u << chunk_bits) < chunks_per_set) chunk_bits++;
+  const unsigned nplanes = 1 + chunk_bits;
+  const unsigned nslices = (chunks_per_set + SLICE - 1) / SLICE;
   const unsigned big_cap = nbuckets / 4 + 16;
   const size_t max_big_chunks = total / BIG_CHUNK + big_cap + 1;
 
-  B200ZK_TRY(ensure(ctx, ctx->msm_digits, total * sizeof(int16_t)));
   B200ZK_TRY(ensure(ctx, ctx->msm_sorted, total * sizeof(unsigned)));
   B200ZK_TRY(ensure(ctx, ctx->msm_counts, (size_t)(nbuckets + 1) * 4));
   B200ZK_TRY(ensure(ctx, ctx->msm_starts, (size_t)(nbuckets + 1) * 4));
   B200ZK_TRY(ensure(ctx, ctx->msm_cursor, (size_t)(nbuckets + 1) * 4));
   B200ZK_TRY(ensure(ctx, ctx->msm_buckets, (size_t)nbuckets * 128));
-  B200ZK_TRY(ensure(ctx, ctx->msm_tmp, ((size_t)sh.W * n1 * 2 + (size_t)sh.W * n2 * 3) * 128));
+  B200ZK_TRY(ensure(ctx, ctx->msm_tmp,
+                    ((size_t)sh.nsets * chunks_per_set * 2 + (size_t)sh.nsets * nplanes * nslices + sh.nsets) * 128));
   B200ZK_TRY(ensure(ctx, ctx->msm_small, sizeof(BigPlan) + (size_t)big_cap * 8 + max_big_chunks * 8));
   B200ZK_TRY(ensure(ctx, ctx->msm_big, max_big_chunks * 128));
   size_t scan_bytes = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (unsigned*)nullptr, (unsigned*)nullptr, (int)(nbuckets + 1), st);
   B200ZK_TRY(ensure(ctx, ctx->msm_scan_tmp, scan_bytes));
 
-  const void* base_ptr = (const char*)bases->dev + first_base * 64;
-  int16_t* digits = (int16_t*)ctx->msm_digits.p;
   unsigned* sorted = (unsigned*)ctx->msm_sorted.p;
   unsigned* counts = (unsigned*)ctx->msm_counts.p;
   unsigned* starts = (unsigned*)ctx->msm_starts.p;
   unsigned* cursor = (unsigned*)ctx->msm_cursor.p;
   char* tmp = (char*)ctx->msm_tmp.p;
-  void* run1 = tmp;
-  void* acc1 = tmp + (size_t)sh.W * n1 * 128;
-  void* asum = tmp + (size_t)sh.W * n1 * 256;
-  void* run2 = (char*)asum + (size_t)sh.W * n2 * 128;
-  void* acc2 = (char*)run2 + (size_t)sh.W * n2 * 128;
+  void* run = tmp;
+  void* acc = tmp + (size_t)sh.nsets * chunks_per_set * 128;
+  void* partial = tmp + (size_t)sh.nsets * chunks_per_set * 256;
+  void* set_sums = (char*)partial + (size_t)sh.nsets * nplanes * nslices * 128;
   BigPlan* plan = (BigPlan*)ctx->msm_small.p;
   unsigned* big_bucket = (unsigned*)((char*)ctx->msm_small.p + sizeof(BigPlan));
   unsigned* big_first = big_bucket + big_cap;
@@ -387,8 +536,8 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
   {
     PhaseTimer pt(ctx, PH_MSM_DIGITS);
     unsigned blocks = (unsigned)((n + 255) / 256);
-    msm_digits_kernel<<<blocks, 256, 0, st>>>((const uint4*)scalars_dev, n, sh, digits, counts);
-    B200ZK_LAUNCH_CHECK(ctx, "msm_digits_kernel");
+    msm_hist_kernel<<<blocks, 256, 0, st>>>((const uint4*)scalars_dev, n, sh, counts);
+    B200ZK_LAUNCH_CHECK(ctx, "msm_hist_kernel");
   }
   {
     PhaseTimer pt(ctx, PH_MSM_SCAN);
@@ -400,8 +549,8 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
   }
   {
     PhaseTimer pt(ctx, PH_MSM_SCATTER);
-    dim3 grid((unsigned)((n + 255) / 256), sh.W);
-    msm_scatter_kernel<<<grid, 256, 0, st>>>(digits, n, sh, cursor, sorted);
+    unsigned blocks = (unsigned)((n + 255) / 256);
+    msm_scatter_kernel<<<blocks, 256, 0, st>>>((const uint4*)scalars_dev, n, sh, cursor, sorted);
     B200ZK_LAUNCH_CHECK(ctx, "msm_scatter_kernel");
   }
   {
@@ -426,16 +575,19 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
   }
   {
     PhaseTimer pt(ctx, PH_MSM_REDUCE);
-    unsigned tot1 = sh.W * n1;
-    msm_reduce_l1_kernel<<<(tot1 + 127) / 128, 128, 0, st>>>(ctx->msm_buckets.p, tot1, run1, acc1);
-    B200ZK_LAUNCH_CHECK(ctx, "msm_reduce_l1_kernel");
-    unsigned tot2 = sh.W * n2;
-    msm_reduce_l2_kernel<<<(tot2 + 127) / 128, 128, 0, st>>>(run1, acc1, n1, n2, sh.W, asum, run2, acc2);
-    B200ZK_LAUNCH_CHECK(ctx, "msm_reduce_l2_kernel");
+    const unsigned tot1 = sh.nsets * chunks_per_set;
+    msm_reduce_r1_kernel<<<(tot1 + 127) / 128, 128, 0, st>>>(ctx->msm_buckets.p, tot1, run, acc);
+    B200ZK_LAUNCH_CHECK(ctx, "msm_reduce_r1_kernel");
+    const size_t shm = BIG_THREADS * sizeof(G1XYZZ);
+    dim3 grid2(nslices, nplanes, sh.nsets);
+    msm_reduce_r2_kernel<<<grid2, BIG_THREADS, shm, st>>>(run, acc, chunks_per_set, nslices, partial);
+    B200ZK_LAUNCH_CHECK(ctx, "msm_reduce_r2_kernel");
+    msm_reduce_r3_kernel<<<sh.nsets, 32 * nplanes, 0, st>>>(partial, nplanes, nslices, set_sums);
+    B200ZK_LAUNCH_CHECK(ctx, "msm_reduce_r3_kernel");
   }
   {
     PhaseTimer pt(ctx, PH_MSM_FINAL);
-    msm_final_kernel<<<1, 64, 0, st>>>(asum, run2, acc2, n2, sh, out_dev, out_kind);
+    msm_final_kernel<<<1, 32, 0, st>>>(set_sums, sh, out_dev, out_kind);
     B200ZK_LAUNCH_CHECK(ctx, "msm_final_kernel");
   }
   return B200ZK_OK;

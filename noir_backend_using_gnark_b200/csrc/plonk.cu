@@ -404,24 +404,36 @@ __global__ void __launch_bounds__(256) k_fold7(FoldArgs a) {
   fe_store(a.out + 2 * j, v);
 }
 
-// foldedHDigest = H0 + zpm*(H1 + zpm*H2)   (two scalar multiplications, one thread)
-__global__ void k_fold_digest(const void* __restrict__ H, FrArg zpm_regular, void* out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// out = sum_k scalars[k] * points[k] for a handful of points (k < 32): lane k does double-and-add over its
+// regular-form scalar, the lanes are summed with a warp-shuffle tree.  Used for the homomorphic digests
+// (folded H, linearised polynomial) that gnark obtains from existing commitments or a full MSM.
+struct SmallMsmArgs {
+  const void* points[8];   // each a G1Affine (64 B) in device memory
+  FrArg scalars[8];        // regular form
+  unsigned count;
+};
+__global__ void k_small_msm(SmallMsmArgs a, void* out) {
+  const unsigned lane = threadIdx.x & 31;
   G1XYZZ acc = g1_xyzz_inf();
-  for (int k = 2; k >= 0; k--) {
-    if (k != 2) {
-      // acc = zpm * acc  (double-and-add over the regular-form scalar)
-      G1XYZZ base = acc;
-      acc = g1_xyzz_inf();
-      for (int b = 255; b >= 0; b--) {
-        g1_double(acc);
-        if ((zpm_regular.l[b >> 5] >> (b & 31)) & 1u) g1_add(acc, base);
-      }
+  if (lane < a.count) {
+    G1Affine p = g1_load_affine(a.points[lane], 0);
+    for (int b = 255; b >= 0; b--) {
+      g1_double(acc);
+      if ((a.scalars[lane].l[b >> 5] >> (b & 31)) & 1u) g1_add_mixed(acc, p);
     }
-    G1Affine hk = g1_load_affine(H, k);
-    g1_add_mixed(acc, hk);
   }
-  g1_store_affine(out, 0, g1_to_affine(acc));
+  for (int d = 16; d > 0; d >>= 1) {
+    G1XYZZ o;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      o.x.l[i] = __shfl_xor_sync(0xffffffffu, acc.x.l[i], d);
+      o.y.l[i] = __shfl_xor_sync(0xffffffffu, acc.y.l[i], d);
+      o.zz.l[i] = __shfl_xor_sync(0xffffffffu, acc.zz.l[i], d);
+      o.zzz.l[i] = __shfl_xor_sync(0xffffffffu, acc.zzz.l[i], d);
+    }
+    g1_add(acc, o);
+  }
+  if (lane == 0) g1_store_affine(out, 0, g1_to_affine(acc));
 }
 
 }  // namespace b200zk
@@ -479,7 +491,7 @@ void carve(b200zk_plonk_pk* pk, char* base, size_t* total) {
   pk->chunks = c.take<uint4>((N4 / 32 + 2048) * 32);
   pk->partials = c.take<uint4>((N4 / (32 * 256) + 64) * 32);
   pk->scal = c.take<uint4>(64 * 32);
-  pk->points = c.take<void>(16 * 64);
+  pk->points = c.take<void>(24 * 64);  // 16 result slots + device copy of the 8 vk points
   *total = c.off;
 }
 
@@ -643,6 +655,7 @@ int b200zk_plonk_setup(b200zk_ctx* ctx, const b200zk_bases* bases, unsigned log2
   const uint4* cpoly[8] = {pk->s1, pk->s2, pk->s3, pk->ql, pk->qr, pk->qm, pk->qo, pk->cqk};
   for (int i = 0; i < 8; i++) PK_TRY(commit(ctx, pk, cpoly[i], n, i));
   PK_TRY(fetch_points(ctx, pk, 0, 8, pk->vk_points));
+  PK_CUDA(cudaMemcpyAsync((char*)pk->points + 64 * 16, pk->points, 8 * 64, cudaMemcpyDeviceToDevice, st));
   // Lagrange-coset forms on the big domain (gnark: computeLagrangeCosetPolys at key load)
   const uint4* csrc[7] = {pk->ql, pk->qr, pk->qm, pk->qo, pk->s1, pk->s2, pk->s3};
   uint4* cdst[7] = {pk->e_ql, pk->e_qr, pk->e_qm, pk->e_qo, pk->e_s1, pk->e_s2, pk->e_s3};
@@ -842,6 +855,7 @@ int b200zk_plonk_prove(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solutio
   const Fe4 lz = sc[0], rz = sc[1], oz = sc[2], s1z = sc[3], s2z = sc[4], zu = sc[5];
 
   // P15: linearised polynomial and its digest
+  Fe4 lin_c_s3, lin_c_z;
   {
     const Fe4 u = host::from_u64(HFR, 5);
     auto M = [&](const Fe4& a, const Fe4& b) { return host::mul(HFR, a, b); };
@@ -864,15 +878,45 @@ int b200zk_plonk_prove(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solutio
     a.l = to_arg(lz); a.r = to_arg(rz); a.o = to_arg(oz); a.lag = to_arg(lagv);
     k_linpol<<<nblocks(n + 3, 256), 256, 0, st>>>(a);
     B200ZK_LAUNCH_CHECK(ctx, "k_linpol");
+    lin_c_s3 = M(alpha, c1);
+    lin_c_z = A(M(alpha, c2), lagv);
   }
-  B200ZK_TRY(commit(ctx, pk, pk->lin, n + 3, 0));  // slot 0: linearised polynomial digest
+  {
+    // digest of the linearised polynomial from the commitments it is a linear combination of (what the verifier
+    // does; equal to kzg.Commit(lin) because the commitment is linear) instead of a full (n+3)-point MSM:
+    //   l*[Ql] + r*[Qr] + l*r*[Qm] + o*[Qo] + [Qk] + alpha*c1*[S3] + (alpha*c2 + lag)*[Z]
+    SmallMsmArgs sm;
+    char* vkd = (char*)pk->points + 64 * 16;  // device copy of the vk points (uploaded at setup)
+    const void* pp[7] = {vkd + 64 * 3, vkd + 64 * 4, vkd + 64 * 5, vkd + 64 * 6, vkd + 64 * 7, vkd + 64 * 2,
+                         (char*)pk->points + 64 * 11};
+    const Fe4 ss[7] = {lz, rz, host::mul(HFR, lz, rz), oz, HFR.one, lin_c_s3, lin_c_z};
+    for (int i = 0; i < 7; i++) {
+      sm.points[i] = pp[i];
+      sm.scalars[i] = to_arg(host::from_mont(HFR, ss[i]));
+    }
+    sm.points[7] = pp[0];
+    sm.scalars[7] = to_arg(Fe4{{0, 0, 0, 0}});
+    sm.count = 7;
+    k_small_msm<<<1, 32, 0, st>>>(sm, (char*)pk->points + 64 * 0);  // slot 0: linearised polynomial digest
+    B200ZK_LAUNCH_CHECK(ctx, "k_small_msm");
+  }
 
   // P16: folded H (polynomial and digest)
   const Fe4 zpm = host::pow_u64(HFR, zeta, (uint64_t)m);
   k_fold_h<<<nblocks(m, 256), 256, 0, st>>>(pk->t, m, to_arg(zpm), pk->folded_h);
   B200ZK_LAUNCH_CHECK(ctx, "k_fold_h");
-  k_fold_digest<<<1, 32, 0, st>>>((char*)pk->points + 64 * 12, to_arg(host::from_mont(HFR, zpm)), (char*)pk->points + 64 * 1);
-  B200ZK_LAUNCH_CHECK(ctx, "k_fold_digest");
+  {
+    // foldedHDigest = H0 + zpm*H1 + zpm^2*H2
+    SmallMsmArgs sm;
+    const Fe4 ss[3] = {HFR.one, zpm, host::mul(HFR, zpm, zpm)};
+    for (int i = 0; i < 8; i++) {
+      sm.points[i] = (char*)pk->points + 64 * (12 + (i < 3 ? i : 0));
+      sm.scalars[i] = to_arg(i < 3 ? host::from_mont(HFR, ss[i]) : Fe4{{0, 0, 0, 0}});
+    }
+    sm.count = 3;
+    k_small_msm<<<1, 32, 0, st>>>(sm, (char*)pk->points + 64 * 1);
+    B200ZK_LAUNCH_CHECK(ctx, "k_small_msm");
+  }
 
   // P17: batch opening at zeta of [foldedH, lin, L, R, O, S1, S2]
   B200ZK_TRY(eval_poly(ctx, pk, pk->folded_h, m, zeta, 6));

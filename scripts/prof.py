@@ -22,6 +22,8 @@ if what == "msm":
         zk.load().b200zk_msm_set_window(ctx.handle, int(sys.argv[4]))
     one = (1).to_bytes(32, "little")
     srs = zk.SRS.NewSRS(n, bytes(raw[0].tobytes()), ctx)
+    if os.environ.get("B200ZK_PRECOMPUTE", "1") == "1" and len(sys.argv) <= 4:
+        srs.precompute()
     out = torch.zeros(64, dtype=torch.uint8, device="cuda")
     for _ in range(reps):
         zk.MultiExp(srs, x, n=n, out=out)

@@ -56,6 +56,8 @@ def main():
     alpha = zkp.fr_to_mont([0x1234567890ABCDEF1234567])
     t0 = time.time()
     srs = zk.SRS.NewSRS(n + 3, alpha, ctx)
+    if "--no-precompute" not in sys.argv:
+        srs.precompute()
     t_srs = time.time() - t0
     t0 = time.time()
     pk = zkp.ProvingKey.SetupRaw(srs, log2n, log2n + 2, 1, c["nb_wires"], c["ql"], c["qr"], c["qm"], c["qo"], c["qk"], c["lro"], ctx)

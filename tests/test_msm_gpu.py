@@ -172,3 +172,37 @@ def test_srs_generate_matches_oracle(ctx):
     assert com == o.g1_to_bytes([o.g1_mul(o.G1_GEN, p_alpha)])
     srs.close()
     shard.close()
+
+
+@pytest.mark.parametrize("log2n,c", [(10, 0), (12, 10), (14, 0), (16, 13), (18, 0)])
+def test_precomputed_window_table(ctx, log2n, c):
+    """b200zk_bases_precompute: same canonical result through the single-bucket-set path (prefixes, shards, skew)."""
+    n = 1 << log2n
+    pts = structured(n).copy()
+    pts[7 * 64: 8 * 64] = 0                      # a point at infinity among the bases
+    sc = cref.random_fr(n, 0xB2000001 + log2n)
+    srs = zk.SRS(pts, ctx)
+    want = cref.msm(pts, sc, n, nthreads=cref.ncores())
+    assert zk.MultiExp(srs, sc) == want          # classic path
+    srs.precompute(c)
+    assert zk.MultiExp(srs, sc) == want          # table path
+    m = n - 5
+    assert zk.MultiExp(srs, sc, n=m) == cref.msm(pts, sc, m, nthreads=cref.ncores())   # kzg.Commit prefix
+    assert zk.MultiExp(srs, sc, n=3) == cref.msm(pts, sc, 3)                            # small n falls back to classic
+    if log2n >= 12:
+        import torch
+
+        d_sc = torch.from_numpy(sc).cuda()
+        torch.cuda.synchronize()
+        half = n // 2
+        parts = torch.empty(256, dtype=torch.uint8, device="cuda")
+        zk.MultiExp(srs, d_sc[: half * 32], n=half, first_base=0, out=parts[:128], partial=True)
+        zk.MultiExp(srs, d_sc[half * 32:], n=half, first_base=half, out=parts[128:], partial=True)
+        res = zk.SumPartials(ctx, parts)
+        ctx.sync()
+        assert res.cpu().numpy().tobytes() == want
+    # skewed scalars through the table path
+    v = o.random_fr(1, 5)[0]
+    eq = np.tile(np.frombuffer(o.fr_to_mont_bytes([v]), dtype=np.uint8), n)
+    assert zk.MultiExp(srs, eq) == cref.msm(pts, eq, n, nthreads=cref.ncores())
+    srs.close()

@@ -25,10 +25,12 @@ def to_product_cs(cs: pl.SparseR1CS) -> zkp.SparseR1CS:
                           [x.qo for x in g], [x.qk for x in g], [x.a for x in g], [x.b for x in g], [x.c for x in g])
 
 
-def check_against_oracle(ctx, cs_o: pl.SparseR1CS, witness, srs_size: int, seed: int):
+def check_against_oracle(ctx, cs_o: pl.SparseR1CS, witness, srs_size: int, seed: int, precompute: bool = False):
     srs_o = pl.SRS(srs_size, ALPHA)
     srs_d = zk.SRS.NewSRS(srs_size, o.fr_to_mont_bytes([ALPHA]), ctx)
     assert srs_d.download() == srs_o.g1_bytes.tobytes()
+    if precompute:
+        srs_d.precompute()
     pk_o = pl.setup(cs_o, srs_o)
     pk_d = zkp.ProvingKey.Setup(to_product_cs(cs_o), srs_d, ctx)
     assert (pk_d.log2n, pk_d.log2n_big) == (pk_o.n.bit_length() - 1, pk_o.n_big.bit_length() - 1)
@@ -60,7 +62,7 @@ def test_synthetic_chain_byte_identical(ctx, gates, nb_public):
     size = 1
     while size < gates + nb_public:
         size <<= 1
-    check_against_oracle(ctx, cs_o, x, size + 3, 0xB2000006)
+    check_against_oracle(ctx, cs_o, x, size + 3, 0xB2000006, precompute=(gates >= 1023))
 
 
 def test_different_blinding_changes_proof_but_verifies(ctx):
@@ -83,7 +85,7 @@ def test_large_circuit_verifies(ctx):
     gates = (1 << 18) - 1
     cs_o, x = pl.synthetic_chain_circuit(gates, 0xB2000004)
     n = 1 << 18
-    srs_d = zk.SRS.NewSRS(n + 3, o.fr_to_mont_bytes([ALPHA]), ctx)
+    srs_d = zk.SRS.NewSRS(n + 3, o.fr_to_mont_bytes([ALPHA]), ctx).precompute()
     pk_d = zkp.ProvingKey.Setup(to_product_cs(cs_o), srs_d, ctx)
     proof = pk_d.Prove(o.fr_to_mont_bytes(x), blinding_bytes(9))
     S = [o.g1_from_bytes(b)[0] for b in pk_d.vk_points]
