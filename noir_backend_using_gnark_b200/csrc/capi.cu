@@ -51,6 +51,13 @@ int b200zk_init(int device, b200zk_ctx** out) {
     delete ctx;
     return B200ZK_ERR_CUDA;
   }
+  if (cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+    cudaGetLastError();
+    delete ctx;
+    return B200ZK_ERR_CUDA;
+  }
   *out = ctx;
   return B200ZK_OK;
 }
@@ -72,6 +79,9 @@ void b200zk_destroy(b200zk_ctx* ctx) {
   free_buf(ctx->msm_scan_tmp);
   free_buf(ctx->msm_big);
   cudaStreamDestroy(ctx->stream);
+  if (ctx->side) cudaStreamDestroy(ctx->side);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   delete ctx;
 }
 

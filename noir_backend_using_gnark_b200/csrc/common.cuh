@@ -53,6 +53,8 @@ struct b200zk_ctx {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t side = nullptr;  // latency-bound single-warp work that overlaps the big kernels (prover digests)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   uint64_t launches = 0;
   char cuda_err[256] = {0};
   int forced_window = 0;

@@ -18,6 +18,7 @@
 //                            bit planes which are summed in parallel (warp-shuffle trees) and recombined by doublings
 //   6 msm_final_kernel       Horner over windows (classic mode only), canonical affine (or XYZZ partial) output
 // The result is a canonical affine point, so it is bit-identical to gnark's for any window size / summation order.
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include "common.cuh"
 #include "g1.cuh"
@@ -111,11 +112,15 @@ __device__ __forceinline__ G1Affine load_signed(const void* bases, unsigned entr
   return p;
 }
 
+// Threads take buckets in order of decreasing run length (`order`), so the 32 runs of a warp have (almost) the same
+// length and the longest runs start first: no lane idles while its neighbours finish.
 __global__ void __launch_bounds__(128) msm_accumulate_kernel(const void* __restrict__ bases, const unsigned* __restrict__ starts,
-                                                             const unsigned* __restrict__ sorted, MsmShape sh,
+                                                             const unsigned* __restrict__ sorted,
+                                                             const unsigned* __restrict__ order, MsmShape sh,
                                                              unsigned nbuckets, void* __restrict__ buckets) {
-  unsigned b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nbuckets) return;
+  unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= nbuckets) return;
+  const unsigned b = order[tid];
   unsigned lo = starts[b], hi = starts[b + 1];
   G1XYZZ acc = g1_xyzz_inf();
   if (hi - lo <= sh.big_len && hi > lo) {
@@ -344,6 +349,11 @@ __global__ void g1_sum_kernel(const void* __restrict__ partials, unsigned count,
   g1_store_affine(out, 0, r);
 }
 
+__global__ void iota_u32_kernel(unsigned* __restrict__ dst, size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (unsigned)i;
+}
+
 __global__ void copy_u32_kernel(const unsigned* __restrict__ src, unsigned* __restrict__ dst, size_t n) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i < n) dst[i] = src[i];
@@ -514,7 +524,16 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
   B200ZK_TRY(ensure(ctx, ctx->msm_big, max_big_chunks * 128));
   size_t scan_bytes = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (unsigned*)nullptr, (unsigned*)nullptr, (int)(nbuckets + 1), st);
+  size_t sort_bytes = 0;
+  cub::DeviceRadixSort::SortPairsDescending(nullptr, sort_bytes, (const unsigned*)nullptr, (unsigned*)nullptr,
+                                            (const unsigned*)nullptr, (unsigned*)nullptr, (int)nbuckets, 0, 32, st);
+  if (sort_bytes > scan_bytes) scan_bytes = sort_bytes;
   B200ZK_TRY(ensure(ctx, ctx->msm_scan_tmp, scan_bytes));
+  // run-length ordering scratch: [iota | sorted lengths (unused) | order]
+  B200ZK_TRY(ensure(ctx, ctx->msm_digits, (size_t)nbuckets * 12));
+  unsigned* iota = (unsigned*)ctx->msm_digits.p;
+  unsigned* len_sorted = iota + nbuckets;
+  unsigned* order = len_sorted + nbuckets;
 
   unsigned* sorted = (unsigned*)ctx->msm_sorted.p;
   unsigned* counts = (unsigned*)ctx->msm_counts.p;
@@ -546,6 +565,12 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
     unsigned blocks = (nbuckets + 1 + 255) / 256;
     copy_u32_kernel<<<blocks, 256, 0, st>>>(starts, cursor, nbuckets + 1);
     B200ZK_LAUNCH_CHECK(ctx, "copy_u32_kernel");
+    iota_u32_kernel<<<blocks, 256, 0, st>>>(iota, nbuckets);
+    B200ZK_LAUNCH_CHECK(ctx, "iota_u32_kernel");
+    size_t sb = ctx->msm_scan_tmp.cap;
+    B200ZK_CUDA(ctx, cub::DeviceRadixSort::SortPairsDescending(ctx->msm_scan_tmp.p, sb, (const unsigned*)counts, len_sorted,
+                                                               (const unsigned*)iota, order, (int)nbuckets, 0, 32, st));
+    ctx->launches += 4;
   }
   {
     PhaseTimer pt(ctx, PH_MSM_SCATTER);
@@ -556,7 +581,7 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
   {
     PhaseTimer pt(ctx, PH_MSM_ACCUMULATE);
     unsigned blocks = (nbuckets + 127) / 128;
-    msm_accumulate_kernel<<<blocks, 128, 0, st>>>(base_ptr, starts, sorted, sh, nbuckets, ctx->msm_buckets.p);
+    msm_accumulate_kernel<<<blocks, 128, 0, st>>>(base_ptr, starts, sorted, order, sh, nbuckets, ctx->msm_buckets.p);
     B200ZK_LAUNCH_CHECK(ctx, "msm_accumulate_kernel");
   }
   {

@@ -849,26 +849,67 @@ int b200zk_plonk_prove(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solutio
   B200ZK_TRY(eval_poly(ctx, pk, pk->s1, n, zeta, 3));
   B200ZK_TRY(eval_poly(ctx, pk, pk->s2, n, zeta, 4));
   B200ZK_TRY(eval_poly(ctx, pk, pk->bz, n + 3, zeta_shift, 5));
-  B200ZK_TRY(divide_x_minus_a(ctx, pk, pk->bz, n + 3, zeta_shift, pk->quot));
-  B200ZK_TRY(commit(ctx, pk, pk->quot, n + 2, 15));  // ZShiftedOpening.H
   B200ZK_TRY(fetch_scalars(ctx, pk, 0, 6, sc));
   const Fe4 lz = sc[0], rz = sc[1], oz = sc[2], s1z = sc[3], s2z = sc[4], zu = sc[5];
 
-  // P15: linearised polynomial and its digest
-  Fe4 lin_c_s3, lin_c_z;
+  // P15/P16 scalars (host)
+  const Fe4 u5 = host::from_u64(HFR, 5);
+  auto M = [&](const Fe4& a, const Fe4& b) { return host::mul(HFR, a, b); };
+  auto A = [&](const Fe4& a, const Fe4& b) { return host::add(HFR, a, b); };
+  Fe4 c1 = M(A(A(M(s1z, beta), lz), gamma), A(A(M(s2z, beta), rz), gamma));
+  c1 = M(M(c1, zu), beta);
+  const Fe4 uz = M(zeta, u5), uuz = M(uz, u5);
+  Fe4 c2 = M(A(A(M(beta, zeta), lz), gamma), A(A(M(beta, uz), rz), gamma));
+  c2 = M(c2, A(A(M(beta, uuz), oz), gamma));
+  c2 = host::neg(HFR, c2);
+  Fe4 lagv = host::sub(HFR, host::pow_u64(HFR, zeta, (uint64_t)n), HFR.one);
+  lagv = M(lagv, host::inv(HFR, host::sub(HFR, zeta, HFR.one)));
+  lagv = M(M(M(lagv, alpha), alpha), host::inv(HFR, host::from_u64(HFR, (uint64_t)n)));
+  const Fe4 zpm = host::pow_u64(HFR, zeta, (uint64_t)m);
+
+  // The two homomorphic digests are single-warp, latency-bound kernels: run them on the side stream so they overlap
+  // the opening MSM below instead of sitting on the critical path.
+  B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+  B200ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
   {
-    const Fe4 u = host::from_u64(HFR, 5);
-    auto M = [&](const Fe4& a, const Fe4& b) { return host::mul(HFR, a, b); };
-    auto A = [&](const Fe4& a, const Fe4& b) { return host::add(HFR, a, b); };
-    Fe4 c1 = M(A(A(M(s1z, beta), lz), gamma), A(A(M(s2z, beta), rz), gamma));
-    c1 = M(M(c1, zu), beta);
-    const Fe4 uz = M(zeta, u), uuz = M(uz, u);
-    Fe4 c2 = M(A(A(M(beta, zeta), lz), gamma), A(A(M(beta, uz), rz), gamma));
-    c2 = M(c2, A(A(M(beta, uuz), oz), gamma));
-    c2 = host::neg(HFR, c2);
-    Fe4 lagv = host::sub(HFR, host::pow_u64(HFR, zeta, (uint64_t)n), HFR.one);
-    lagv = M(lagv, host::inv(HFR, host::sub(HFR, zeta, HFR.one)));
-    lagv = M(M(M(lagv, alpha), alpha), host::inv(HFR, host::from_u64(HFR, (uint64_t)n)));
+    // digest of the linearised polynomial from the commitments it is a linear combination of (what the verifier
+    // does; equal to kzg.Commit(lin) because the commitment is linear) instead of a full (n+3)-point MSM:
+    //   l*[Ql] + r*[Qr] + l*r*[Qm] + o*[Qo] + [Qk] + alpha*c1*[S3] + (alpha*c2 + lag)*[Z]
+    SmallMsmArgs sm;
+    char* vkd = (char*)pk->points + 64 * 16;  // device copy of the vk points (uploaded at setup)
+    const void* pp[7] = {vkd + 64 * 3, vkd + 64 * 4, vkd + 64 * 5, vkd + 64 * 6, vkd + 64 * 7, vkd + 64 * 2,
+                         (char*)pk->points + 64 * 11};
+    const Fe4 ss[7] = {lz, rz, M(lz, rz), oz, HFR.one, M(alpha, c1), A(M(alpha, c2), lagv)};
+    for (int i = 0; i < 7; i++) {
+      sm.points[i] = pp[i];
+      sm.scalars[i] = to_arg(host::from_mont(HFR, ss[i]));
+    }
+    sm.points[7] = pp[0];
+    sm.scalars[7] = to_arg(Fe4{{0, 0, 0, 0}});
+    sm.count = 7;
+    k_small_msm<<<1, 32, 0, ctx->side>>>(sm, (char*)pk->points + 64 * 0);  // slot 0: linearised polynomial digest
+    B200ZK_LAUNCH_CHECK(ctx, "k_small_msm");
+  }
+  {
+    // foldedHDigest = H0 + zpm*H1 + zpm^2*H2
+    SmallMsmArgs sm;
+    const Fe4 ss[3] = {HFR.one, zpm, M(zpm, zpm)};
+    for (int i = 0; i < 8; i++) {
+      sm.points[i] = (char*)pk->points + 64 * (12 + (i < 3 ? i : 0));
+      sm.scalars[i] = to_arg(i < 3 ? host::from_mont(HFR, ss[i]) : Fe4{{0, 0, 0, 0}});
+    }
+    sm.count = 3;
+    k_small_msm<<<1, 32, 0, ctx->side>>>(sm, (char*)pk->points + 64 * 1);
+    B200ZK_LAUNCH_CHECK(ctx, "k_small_msm");
+  }
+  B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side));
+
+  // P14: opening of Z at w*zeta
+  B200ZK_TRY(divide_x_minus_a(ctx, pk, pk->bz, n + 3, zeta_shift, pk->quot));
+  B200ZK_TRY(commit(ctx, pk, pk->quot, n + 2, 15));  // ZShiftedOpening.H
+
+  // P15: linearised polynomial
+  {
     LinArgs a;
     a.bz = pk->bz; a.s3 = pk->s3; a.qm = pk->qm; a.ql = pk->ql; a.qr = pk->qr; a.qo = pk->qo; a.cqk = pk->cqk;
     a.out = pk->lin;
@@ -878,49 +919,16 @@ int b200zk_plonk_prove(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solutio
     a.l = to_arg(lz); a.r = to_arg(rz); a.o = to_arg(oz); a.lag = to_arg(lagv);
     k_linpol<<<nblocks(n + 3, 256), 256, 0, st>>>(a);
     B200ZK_LAUNCH_CHECK(ctx, "k_linpol");
-    lin_c_s3 = M(alpha, c1);
-    lin_c_z = A(M(alpha, c2), lagv);
-  }
-  {
-    // digest of the linearised polynomial from the commitments it is a linear combination of (what the verifier
-    // does; equal to kzg.Commit(lin) because the commitment is linear) instead of a full (n+3)-point MSM:
-    //   l*[Ql] + r*[Qr] + l*r*[Qm] + o*[Qo] + [Qk] + alpha*c1*[S3] + (alpha*c2 + lag)*[Z]
-    SmallMsmArgs sm;
-    char* vkd = (char*)pk->points + 64 * 16;  // device copy of the vk points (uploaded at setup)
-    const void* pp[7] = {vkd + 64 * 3, vkd + 64 * 4, vkd + 64 * 5, vkd + 64 * 6, vkd + 64 * 7, vkd + 64 * 2,
-                         (char*)pk->points + 64 * 11};
-    const Fe4 ss[7] = {lz, rz, host::mul(HFR, lz, rz), oz, HFR.one, lin_c_s3, lin_c_z};
-    for (int i = 0; i < 7; i++) {
-      sm.points[i] = pp[i];
-      sm.scalars[i] = to_arg(host::from_mont(HFR, ss[i]));
-    }
-    sm.points[7] = pp[0];
-    sm.scalars[7] = to_arg(Fe4{{0, 0, 0, 0}});
-    sm.count = 7;
-    k_small_msm<<<1, 32, 0, st>>>(sm, (char*)pk->points + 64 * 0);  // slot 0: linearised polynomial digest
-    B200ZK_LAUNCH_CHECK(ctx, "k_small_msm");
   }
 
-  // P16: folded H (polynomial and digest)
-  const Fe4 zpm = host::pow_u64(HFR, zeta, (uint64_t)m);
+  // P16: folded H polynomial
   k_fold_h<<<nblocks(m, 256), 256, 0, st>>>(pk->t, m, to_arg(zpm), pk->folded_h);
   B200ZK_LAUNCH_CHECK(ctx, "k_fold_h");
-  {
-    // foldedHDigest = H0 + zpm*H1 + zpm^2*H2
-    SmallMsmArgs sm;
-    const Fe4 ss[3] = {HFR.one, zpm, host::mul(HFR, zpm, zpm)};
-    for (int i = 0; i < 8; i++) {
-      sm.points[i] = (char*)pk->points + 64 * (12 + (i < 3 ? i : 0));
-      sm.scalars[i] = to_arg(i < 3 ? host::from_mont(HFR, ss[i]) : Fe4{{0, 0, 0, 0}});
-    }
-    sm.count = 3;
-    k_small_msm<<<1, 32, 0, st>>>(sm, (char*)pk->points + 64 * 1);
-    B200ZK_LAUNCH_CHECK(ctx, "k_small_msm");
-  }
 
   // P17: batch opening at zeta of [foldedH, lin, L, R, O, S1, S2]
   B200ZK_TRY(eval_poly(ctx, pk, pk->folded_h, m, zeta, 6));
   B200ZK_TRY(eval_poly(ctx, pk, pk->lin, n + 3, zeta, 7));
+  B200ZK_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));  // join the side stream (digests)
   B200ZK_TRY(fetch_scalars(ctx, pk, 6, 2, sc + 6));
   B200ZK_TRY(fetch_points(ctx, pk, 0, 2, pts + 64 * 9));  // pts[9] = lin digest, pts[10] = folded H digest
   B200ZK_TRY(fetch_points(ctx, pk, 15, 1, pts + 64 * 8));  // pts[8] = ZShiftedOpening.H
