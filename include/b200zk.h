@@ -74,6 +74,8 @@ int b200zk_ntt_dev(b200zk_ctx* ctx, void* a_dev, unsigned log2n, int inverse, in
  * Same inverse / coset semantics as b200zk_ntt (scalings are applied in the half that owns the first / last stage). */
 int b200zk_ntt_dist_half_dev(b200zk_ctx* ctx, const void* src_dev, void* dst_dev, unsigned log2n, unsigned log2g,
                              unsigned rank, unsigned log2c, int half, int inverse, int decimation, int coset);
+/* tests / tuning: force the plain radix-2 pass kernel instead of the radix-4 register kernel (same results) */
+int b200zk_ntt_set_radix2(b200zk_ctx* ctx, int on);
 /* fft.BitReverse(a): in-place index bit-reversal permutation. */
 int b200zk_bit_reverse(b200zk_ctx* ctx, void* a_host, unsigned log2n);
 int b200zk_bit_reverse_dev(b200zk_ctx* ctx, void* a_dev, unsigned log2n);

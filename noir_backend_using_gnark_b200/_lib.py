@@ -53,6 +53,7 @@ def load() -> C.CDLL:
         "b200zk_ntt": (i, [vp, vp, u, i, i, i]),
         "b200zk_ntt_dev": (i, [vp, vp, u, i, i, i]),
         "b200zk_ntt_dist_half_dev": (i, [vp, vp, vp, u, u, u, u, i, i, i, i]),
+        "b200zk_ntt_set_radix2": (i, [vp, i]),
         "b200zk_bit_reverse": (i, [vp, vp, u]),
         "b200zk_bit_reverse_dev": (i, [vp, vp, u]),
         "b200zk_bases_upload": (i, [vp, vp, sz, C.POINTER(vp)]),

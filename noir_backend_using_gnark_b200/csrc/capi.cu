@@ -318,6 +318,12 @@ int b200zk_microbench(b200zk_ctx* ctx, int which, double* out_ops_per_s) {
   return microbench_run(ctx, which, out_ops_per_s);
 }
 
+int b200zk_ntt_set_radix2(b200zk_ctx* ctx, int on) {
+  if (!ctx) return B200ZK_ERR_BAD_ARG;
+  ctx->ntt_radix2 = on != 0;
+  return B200ZK_OK;
+}
+
 int b200zk_msm_set_window(b200zk_ctx* ctx, int c) {
   if (!ctx || (c != 0 && (c < 6 || c > 16))) return B200ZK_ERR_BAD_ARG;
   ctx->forced_window = c;

@@ -58,6 +58,7 @@ struct b200zk_ctx {
   uint64_t launches = 0;
   char cuda_err[256] = {0};
   int forced_window = 0;
+  int ntt_radix2 = 0;  // tests: force the radix-2 pass kernel
   bool profiling = false;
   std::vector<b200zk::PhaseRecord> records;
   b200zk::NttDomain domains[B200ZK_MAX_LOG2N + 1];

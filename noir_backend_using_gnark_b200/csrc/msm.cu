@@ -294,18 +294,20 @@ __device__ __forceinline__ G1XYZZ warp_sum_xyzz(G1XYZZ v) {
   return v;
 }
 
-// grid = sets, block = 32 * nplanes threads
-__global__ void msm_reduce_r3_kernel(const void* __restrict__ partial, unsigned nplanes, unsigned nslices,
-                                     void* __restrict__ set_sums) {
+// grid = sets, block = 8 warps; warp w finishes planes w, w+8, ...
+__global__ void __launch_bounds__(256) msm_reduce_r3_kernel(const void* __restrict__ partial, unsigned nplanes,
+                                                            unsigned nslices, void* __restrict__ set_sums) {
   __shared__ G1XYZZ plane_sum[MAX_PLANES];
-  const unsigned set = blockIdx.x, plane = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  G1XYZZ acc = g1_xyzz_inf();
-  for (unsigned s = lane; s < nslices; s += 32) {
-    G1XYZZ q = g1_load_xyzz(partial, ((size_t)set * nplanes + plane) * nslices + s);
-    g1_add(acc, q);
+  const unsigned set = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (unsigned plane = warp; plane < nplanes; plane += 8) {
+    G1XYZZ acc = g1_xyzz_inf();
+    for (unsigned s = lane; s < nslices; s += 32) {
+      G1XYZZ q = g1_load_xyzz(partial, ((size_t)set * nplanes + plane) * nslices + s);
+      g1_add(acc, q);
+    }
+    acc = warp_sum_xyzz(acc);
+    if (lane == 0) plane_sum[plane] = acc;
   }
-  acc = warp_sum_xyzz(acc);
-  if (lane == 0) plane_sum[plane] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {
     G1XYZZ s = g1_xyzz_inf();
@@ -607,7 +609,7 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
     dim3 grid2(nslices, nplanes, sh.nsets);
     msm_reduce_r2_kernel<<<grid2, BIG_THREADS, shm, st>>>(run, acc, chunks_per_set, nslices, partial);
     B200ZK_LAUNCH_CHECK(ctx, "msm_reduce_r2_kernel");
-    msm_reduce_r3_kernel<<<sh.nsets, 32 * nplanes, 0, st>>>(partial, nplanes, nslices, set_sums);
+    msm_reduce_r3_kernel<<<sh.nsets, 256, 0, st>>>(partial, nplanes, nslices, set_sums);
     B200ZK_LAUNCH_CHECK(ctx, "msm_reduce_r3_kernel");
   }
   {

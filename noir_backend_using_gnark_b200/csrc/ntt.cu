@@ -263,6 +263,160 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(const uint4* __restrict__
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// radix-4 pass kernel: every thread keeps 4 elements in registers and runs TWO stages per shared-memory round trip
+// (3 twiddle loads per 4 butterflies: the second stage's two butterflies share one twiddle).  The first round reads
+// its elements straight from global memory and the last one writes straight back, so a pass of k stages makes
+// ceil(k/2)-1 shared-memory exchanges instead of k+1.  Same PassParams / tiling as ntt_pass_kernel.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void smem_put(uint4* s_lo, uint4* s_hi, unsigned e, const Fr& v) {
+  s_lo[e] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+  s_hi[e] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+__device__ __forceinline__ Fr smem_get(const uint4* s_lo, const uint4* s_hi, unsigned e) {
+  uint4 x = s_lo[e], y = s_hi[e];
+  Fr v;
+  v.l[0] = x.x; v.l[1] = x.y; v.l[2] = x.z; v.l[3] = x.w;
+  v.l[4] = y.x; v.l[5] = y.y; v.l[6] = y.z; v.l[7] = y.w;
+  return v;
+}
+
+// twiddle for the butterfly whose lower element has logical index g, at local half-distance bit hl
+__device__ __forceinline__ Fr stage_twiddle(const PassParams& p, size_t g, unsigned hl, bool& is_one) {
+  const unsigned hbit = hl + (hl >= p.gap_pos ? p.gap_bits : 0u);
+  is_one = hbit == 0;
+  if (is_one) return fe_one<FrParams>();
+  const size_t j = g & (((size_t)1 << hbit) - 1);
+  return fe_load_ro<FrParams>(p.tw + 2 * (j << (p.n - 1 - hbit)));
+}
+
+template <bool DIT>
+__global__ void __launch_bounds__(256) ntt_pass4_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst,
+                                                        PassParams p) {
+  extern __shared__ uint4 smem[];
+  const unsigned tlog = p.k + p.cb;
+  const unsigned T = 1u << tlog;
+  uint4* s_lo = smem;
+  uint4* s_hi = smem + T;
+  const size_t tile = blockIdx.x;
+  const unsigned u = threadIdx.x;  // T/4 threads
+  const unsigned cmask = (1u << p.cb) - 1u;
+  const unsigned c = u & cmask;
+  const unsigned nrounds = (p.k + 1) >> 1;
+  Fr a[4];
+  unsigned rows[4];
+
+  for (unsigned rd = 0; rd < nrounds; rd++) {
+    // dbits handled by this round: a pair (q+1, q), or a single bit q when k is odd (last DIF / last DIT round)
+    unsigned q;
+    bool pair;
+    if (DIT) {
+      q = 2 * rd;
+      pair = q + 1 < p.k;
+    } else {
+      pair = p.k >= 2 * (rd + 1);
+      q = pair ? p.k - 2 * (rd + 1) : 0;
+    }
+    if (pair) {
+      const unsigned rb = u >> p.cb;  // k-2 bits
+      const unsigned base = ((rb >> q) << (q + 2)) | (rb & ((1u << q) - 1u));
+#pragma unroll
+      for (int m = 0; m < 4; m++) rows[m] = base | ((unsigned)m << q);
+    } else {
+      // two independent radix-2 butterflies per thread: (rows[0], rows[1]) and (rows[2], rows[3])
+      const unsigned rb = (u >> p.cb) << 1;  // butterfly ids rb, rb+1 (k-1 bits each)
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const unsigned b = rb + h;
+        const unsigned r0 = ((b >> q) << (q + 1)) | (b & ((1u << q) - 1u));
+        rows[2 * h] = r0;
+        rows[2 * h + 1] = r0 | (1u << q);
+      }
+    }
+    // ---- fetch the 4 elements
+    if (rd == 0) {
+#pragma unroll
+      for (int m = 0; m < 4; m++) {
+        const size_t l = tile_to_local(p, tile, rows[m], c);
+        const size_t addr = p.src_perm ? permuted(p, l) : l;
+        a[m] = fe_load<FrParams>(src + 2 * addr);
+        if (p.scale == SCALE_PRE_COSET) a[m] = fe_mul(a[m], coset_factor(p, local_to_logical(p, l)));
+      }
+    } else {
+      __syncthreads();
+#pragma unroll
+      for (int m = 0; m < 4; m++) a[m] = smem_get(s_lo, s_hi, (rows[m] << p.cb) | c);
+    }
+    // ---- butterflies
+    const size_t g0 = local_to_logical(p, tile_to_local(p, tile, rows[0], c));
+    bool one;
+    if (pair) {
+      const size_t g1 = local_to_logical(p, tile_to_local(p, tile, rows[1], c));
+      const unsigned h_lo = p.L + q, h_hi = p.L + q + 1;
+      if (DIT) {
+        // stage q: (a0,a1), (a2,a3) share one twiddle; stage q+1: (a0,a2) and (a1,a3)
+        Fr t = stage_twiddle(p, g0, h_lo, one);
+        Fr v1 = one ? a[1] : fe_mul(a[1], t);
+        Fr v3 = one ? a[3] : fe_mul(a[3], t);
+        Fr b0 = fe_add(a[0], v1), b1 = fe_sub(a[0], v1), b2 = fe_add(a[2], v3), b3 = fe_sub(a[2], v3);
+        Fr t0 = stage_twiddle(p, g0, h_hi, one);
+        Fr t1 = stage_twiddle(p, g1, h_hi, one);
+        Fr w2 = fe_mul(b2, t0), w3 = fe_mul(b3, t1);
+        a[0] = fe_add(b0, w2); a[2] = fe_sub(b0, w2);
+        a[1] = fe_add(b1, w3); a[3] = fe_sub(b1, w3);
+      } else {
+        // stage q+1: (a0,a2) and (a1,a3); stage q: (a0,a1), (a2,a3) share one twiddle
+        Fr t0 = stage_twiddle(p, g0, h_hi, one);
+        Fr t1 = stage_twiddle(p, g1, h_hi, one);
+        Fr b0 = fe_add(a[0], a[2]), b2 = fe_mul(fe_sub(a[0], a[2]), t0);
+        Fr b1 = fe_add(a[1], a[3]), b3 = fe_mul(fe_sub(a[1], a[3]), t1);
+        Fr t = stage_twiddle(p, g0, h_lo, one);
+        a[0] = fe_add(b0, b1);
+        a[1] = fe_sub(b0, b1);
+        a[2] = fe_add(b2, b3);
+        a[3] = fe_sub(b2, b3);
+        if (!one) {
+          a[1] = fe_mul(a[1], t);
+          a[3] = fe_mul(a[3], t);
+        }
+      }
+    } else {
+      const size_t g2 = local_to_logical(p, tile_to_local(p, tile, rows[2], c));
+      const unsigned hl = p.L + q;
+      bool one2;
+      Fr t0 = stage_twiddle(p, g0, hl, one);
+      Fr t2 = stage_twiddle(p, g2, hl, one2);
+      if (DIT) {
+        Fr v1 = one ? a[1] : fe_mul(a[1], t0);
+        Fr v3 = one2 ? a[3] : fe_mul(a[3], t2);
+        Fr x0 = fe_add(a[0], v1), x1 = fe_sub(a[0], v1), x2 = fe_add(a[2], v3), x3 = fe_sub(a[2], v3);
+        a[0] = x0; a[1] = x1; a[2] = x2; a[3] = x3;
+      } else {
+        Fr x0 = fe_add(a[0], a[1]), x1 = fe_sub(a[0], a[1]), x2 = fe_add(a[2], a[3]), x3 = fe_sub(a[2], a[3]);
+        a[0] = x0; a[2] = x2;
+        a[1] = one ? x1 : fe_mul(x1, t0);
+        a[3] = one2 ? x3 : fe_mul(x3, t2);
+      }
+    }
+    // ---- hand the elements to the next round, or write the tile back
+    if (rd + 1 < nrounds) {
+      if (rd != 0) __syncthreads();  // everyone has read its elements of this round
+#pragma unroll
+      for (int m = 0; m < 4; m++) smem_put(s_lo, s_hi, (rows[m] << p.cb) | c, a[m]);
+    } else {
+#pragma unroll
+      for (int m = 0; m < 4; m++) {
+        const size_t l = tile_to_local(p, tile, rows[m], c);
+        Fr v = a[m];
+        if (p.scale == SCALE_POST_NINV) v = fe_mul(v, fe_load_ro<FrParams>(p.ninv));
+        if (p.scale == SCALE_POST_COSET) v = fe_mul(v, coset_factor(p, local_to_logical(p, l)));
+        const size_t addr = p.dst_perm ? permuted(p, l) : l;
+        fe_store(dst + 2 * addr, v);
+      }
+    }
+  }
+}
+
 __global__ void bit_reverse_kernel(uint4* a, unsigned log2n) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >> log2n) return;
@@ -367,10 +521,18 @@ static int run_slice(b200zk_ctx* ctx, const void* src, void* dst, const NttSlice
     const unsigned tiles = (unsigned)(((size_t)1 << sl.nl) >> tlog);
     const size_t shmem = (size_t)T * 32;
     PhaseTimer pt(ctx, PH_NTT_PASS);
-    if (dit)
+    if (tlog >= 4 && p.k >= 2 && !ctx->ntt_radix2) {
+      // radix-4 kernel: T/4 threads, 4 elements per thread (in-place tiles: every CTA reads its whole tile before
+      // it writes, and tiles are disjoint, so src == dst is safe)
+      if (dit)
+        ntt_pass4_kernel<true><<<tiles, T / 4, shmem, ctx->stream>>>((const uint4*)in, (uint4*)out, p);
+      else
+        ntt_pass4_kernel<false><<<tiles, T / 4, shmem, ctx->stream>>>((const uint4*)in, (uint4*)out, p);
+    } else if (dit) {
       ntt_pass_kernel<true><<<tiles, threads, shmem, ctx->stream>>>((const uint4*)in, (uint4*)out, p);
-    else
+    } else {
       ntt_pass_kernel<false><<<tiles, threads, shmem, ctx->stream>>>((const uint4*)in, (uint4*)out, p);
+    }
     B200ZK_LAUNCH_CHECK(ctx, "ntt_pass_kernel");
     done += p.k;
   }

@@ -176,3 +176,16 @@ def test_four_step_halves_emulated_on_one_gpu(ctx, log2n, world, log2c):
         got = lay.gather([x.cpu().numpy() for x in xs], column_block=(dec == zk.DIT))
         want = cref.ntt(full, log2n, inv, dec, cos, cref.ncores())
         assert got.tobytes() == want, (log2n, world, inv, dec, cos)
+
+
+def test_radix2_and_radix4_kernels_agree(ctx):
+    """both pass kernels (radix-4 register kernel and the plain radix-2 one) against the oracle"""
+    lib = zk.load()
+    for log2n in (5, 11, 15, 19):
+        a = cref.random_fr(1 << log2n, 0xB2000003 + log2n)
+        for inv, dec, cos in VARIANTS:
+            want = cref.ntt(a, log2n, inv, dec, cos, nthreads=cref.ncores())
+            for r2 in (1, 0):
+                lib.b200zk_ntt_set_radix2(ctx.handle, r2)
+                assert run_gpu(ctx, a, log2n, inv, dec, cos).tobytes() == want, (log2n, inv, dec, cos, r2)
+    lib.b200zk_ntt_set_radix2(ctx.handle, 0)
