@@ -291,7 +291,7 @@ __device__ __forceinline__ Fr stage_twiddle(const PassParams& p, size_t g, unsig
 }
 
 template <bool DIT>
-__global__ void __launch_bounds__(256) ntt_pass4_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst,
+__global__ void __launch_bounds__(256, 3) ntt_pass4_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst,
                                                         PassParams p) {
   extern __shared__ uint4 smem[];
   const unsigned tlog = p.k + p.cb;
