@@ -79,12 +79,20 @@ __device__ __forceinline__ Fr load_scalar_regular(const uint4* __restrict__ scal
 __global__ void __launch_bounds__(256) msm_hist_kernel(const uint4* __restrict__ scalars, size_t n, MsmShape sh,
                                                        unsigned* __restrict__ counts) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const unsigned active = __ballot_sync(0xffffffffu, i < n);
   if (i >= n) return;
+  const unsigned lane = threadIdx.x & 31;
   Fr s = load_scalar_regular(scalars, i);
   for_each_digit(s, sh, [&](unsigned w, int d) {
-    if (d != 0) {
-      unsigned mag = d < 0 ? (unsigned)(-d) : (unsigned)d;
-      atomicAdd(&counts[w * sh.key_stride + (mag - 1)], 1u);
+    const unsigned mag = d < 0 ? (unsigned)(-d) : (unsigned)d;
+    const unsigned key = w * sh.key_stride + (mag - 1);
+    if (w + 1 == sh.W) {
+      // the top window holds only 254 - c*(W-1) scalar bits: few distinct buckets, so the lanes of a warp collide
+      // on the same counters -> aggregate per warp (one atomic per distinct bucket)
+      const unsigned grp = __match_any_sync(active, d != 0 ? key : 0xffffffffu);
+      if (d != 0 && lane == (unsigned)(__ffs(grp) - 1)) atomicAdd(&counts[key], (unsigned)__popc(grp));
+    } else if (d != 0) {
+      atomicAdd(&counts[key], 1u);
     }
   });
 }
@@ -92,13 +100,25 @@ __global__ void __launch_bounds__(256) msm_hist_kernel(const uint4* __restrict__
 __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint4* __restrict__ scalars, size_t n, MsmShape sh,
                                                           unsigned* __restrict__ cursor, unsigned* __restrict__ sorted) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const unsigned active = __ballot_sync(0xffffffffu, i < n);
   if (i >= n) return;
+  const unsigned lane = threadIdx.x & 31;
   Fr s = load_scalar_regular(scalars, i);
   for_each_digit(s, sh, [&](unsigned w, int d) {
-    if (d != 0) {
-      unsigned mag = d < 0 ? (unsigned)(-d) : (unsigned)d;
-      unsigned pos = atomicAdd(&cursor[w * sh.key_stride + (mag - 1)], 1u);
-      sorted[pos] = (w * sh.tab_stride + sh.first + (unsigned)i) | (d < 0 ? 0x80000000u : 0u);
+    const unsigned mag = d < 0 ? (unsigned)(-d) : (unsigned)d;
+    const unsigned key = w * sh.key_stride + (mag - 1);
+    const unsigned entry = (w * sh.tab_stride + sh.first + (unsigned)i) | (d < 0 ? 0x80000000u : 0u);
+    if (w + 1 == sh.W) {
+      // warp-aggregated cursor bump for the narrow top window (see msm_hist_kernel)
+      const unsigned grp = __match_any_sync(active, d != 0 ? key : 0xffffffffu);
+      const unsigned leader = (unsigned)(__ffs(grp) - 1);
+      unsigned base = 0;
+      if (d != 0 && lane == leader) base = atomicAdd(&cursor[key], (unsigned)__popc(grp));
+      base = __shfl_sync(grp, base, leader);
+      if (d != 0) sorted[base + __popc(grp & ((1u << lane) - 1u))] = entry;
+    } else if (d != 0) {
+      unsigned pos = atomicAdd(&cursor[key], 1u);
+      sorted[pos] = entry;
     }
   });
 }
@@ -124,8 +144,14 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const void* __restr
   unsigned lo = starts[b], hi = starts[b + 1];
   G1XYZZ acc = g1_xyzz_inf();
   if (hi - lo <= sh.big_len && hi > lo) {
+    // software pipeline of the random 64-byte gathers: the point for step j+1 is loaded into registers while step j
+    // adds, and the line for step j+3 is pulled into L2 (the window table is far larger than L2 and the TLB reach)
     G1Affine cur = load_signed(bases, sorted[lo]);
     for (unsigned j = lo + 1; j < hi; j++) {
+      if (j + 2 < hi) {
+        const char* ahead = reinterpret_cast<const char*>(bases) + (size_t)(sorted[j + 2] & 0x7fffffffu) * 64;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ahead));
+      }
       G1Affine nxt = load_signed(bases, sorted[j]);
       g1_add_mixed(acc, cur);
       cur = nxt;
@@ -179,7 +205,26 @@ __device__ __forceinline__ void block_reduce_xyzz(G1XYZZ& acc, G1XYZZ* sh_pts) {
   __syncthreads();
 }
 
-// grid-stride over chunk descriptors: one CTA sums one chunk of a long run
+__device__ __forceinline__ G1XYZZ warp_sum_xyzz(G1XYZZ v) {
+  // butterfly reduction with warp shuffles: every 32-bit limb of the point travels by __shfl_xor_sync
+  for (int d = 16; d > 0; d >>= 1) {
+    G1XYZZ o;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      o.x.l[i] = __shfl_xor_sync(0xffffffffu, v.x.l[i], d);
+      o.y.l[i] = __shfl_xor_sync(0xffffffffu, v.y.l[i], d);
+      o.zz.l[i] = __shfl_xor_sync(0xffffffffu, v.zz.l[i], d);
+      o.zzz.l[i] = __shfl_xor_sync(0xffffffffu, v.zzz.l[i], d);
+    }
+    // both partners compute the same group element (the XYZZ representative may differ between partners,
+    // which is fine: only lane 0's value is used)
+    g1_add(v, o);
+  }
+  return v;
+}
+
+// grid-stride over chunk descriptors: one WARP sums one chunk of a long run (lane-serial mixed additions, then a
+// warp-shuffle tree: 5 full additions of overhead per chunk instead of a shared-memory tree per CTA)
 __global__ void __launch_bounds__(BIG_THREADS) msm_big_accumulate_kernel(const void* __restrict__ bases,
                                                                          const unsigned* __restrict__ starts,
                                                                          const unsigned* __restrict__ sorted,
@@ -187,21 +232,27 @@ __global__ void __launch_bounds__(BIG_THREADS) msm_big_accumulate_kernel(const v
                                                                          const unsigned* __restrict__ chunk_bucket,
                                                                          const unsigned* __restrict__ chunk_idx,
                                                                          void* __restrict__ partials) {
-  extern __shared__ uint4 big_smem[];
-  G1XYZZ* sh_pts = reinterpret_cast<G1XYZZ*>(big_smem);
   const unsigned nchunks = plan->nchunks;
-  for (unsigned item = blockIdx.x; item < nchunks; item += gridDim.x) {
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned warps_per_cta = BIG_THREADS / 32;
+  for (unsigned item = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); item < nchunks; item += gridDim.x * warps_per_cta) {
     const unsigned b = chunk_bucket[item];
     const unsigned lo = starts[b], hi = starts[b + 1];
     unsigned clo = lo + chunk_idx[item] * BIG_CHUNK;
     unsigned chi = clo + BIG_CHUNK < hi ? clo + BIG_CHUNK : hi;
     G1XYZZ acc = g1_xyzz_inf();
-    for (unsigned j = clo + threadIdx.x; j < chi; j += BIG_THREADS) {
-      G1Affine p = load_signed(bases, sorted[j]);
-      g1_add_mixed(acc, p);
+    unsigned j = clo + lane;
+    if (j < chi) {
+      G1Affine cur = load_signed(bases, sorted[j]);
+      for (j += 32; j < chi; j += 32) {
+        G1Affine nxt = load_signed(bases, sorted[j]);  // in flight while the addition below runs
+        g1_add_mixed(acc, cur);
+        cur = nxt;
+      }
+      g1_add_mixed(acc, cur);
     }
-    block_reduce_xyzz(acc, sh_pts);
-    if (threadIdx.x == 0) g1_store_xyzz(partials, item, acc);
+    acc = warp_sum_xyzz(acc);
+    if (lane == 0) g1_store_xyzz(partials, item, acc);
   }
 }
 
@@ -274,24 +325,6 @@ __global__ void __launch_bounds__(BIG_THREADS) msm_reduce_r2_kernel(const void* 
   }
   block_reduce_xyzz(acc, sh_pts);
   if (threadIdx.x == 0) g1_store_xyzz(partial, ((size_t)set * gridDim.y + plane) * nslices + slice, acc);
-}
-
-__device__ __forceinline__ G1XYZZ warp_sum_xyzz(G1XYZZ v) {
-  // butterfly reduction with warp shuffles: every 32-bit limb of the point travels by __shfl_xor_sync
-  for (int d = 16; d > 0; d >>= 1) {
-    G1XYZZ o;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-      o.x.l[i] = __shfl_xor_sync(0xffffffffu, v.x.l[i], d);
-      o.y.l[i] = __shfl_xor_sync(0xffffffffu, v.y.l[i], d);
-      o.zz.l[i] = __shfl_xor_sync(0xffffffffu, v.zz.l[i], d);
-      o.zzz.l[i] = __shfl_xor_sync(0xffffffffu, v.zzz.l[i], d);
-    }
-    // both partners compute the same group element (the XYZZ representative may differ between partners,
-    // which is fine: only lane 0's value is used)
-    g1_add(v, o);
-  }
-  return v;
 }
 
 // grid = sets, block = 8 warps; warp w finishes planes w, w+8, ...
@@ -413,14 +446,12 @@ static unsigned choose_window(size_t n) {
   unsigned lg = 0;
   while (((size_t)1 << (lg + 1)) <= n) lg++;
   // fewer, larger windows as n grows; at least 2^5 buckets so the 32-wide reduction chunks are full
+  // window sizes whose TOP window still holds >= 7 scalar bits (254 - c*(W-1)): c = 12, 14, 18, 21, 23 leave 1-2 bits
+  // there, which funnels n entries into <= 3 buckets (long-run path + atomic contention)
   if (lg >= 23) return 16;
-  if (lg >= 21) return 15;
-  if (lg >= 19) return 14;
-  if (lg >= 17) return 13;
-  if (lg >= 15) return 12;
-  if (lg >= 13) return 11;
+  if (lg >= 19) return 15;
+  if (lg >= 15) return 13;
   if (lg >= 11) return 10;
-  if (lg >= 9) return 9;
   return 8;
 }
 
@@ -431,7 +462,13 @@ int msm_precompute_run(b200zk_ctx* ctx, b200zk_bases* bases, int c_req) {
   if (n < 1024) return B200ZK_OK;  // not worth it: the classic path is used
   unsigned lg = 0;
   while (((size_t)1 << (lg + 1)) <= n) lg++;
-  unsigned c = c_req ? (unsigned)c_req : lg - 2;
+  unsigned c;
+  if (c_req) c = (unsigned)c_req;
+  else if (lg >= 23) c = 22;   // W = 12, top window 12 bits
+  else if (lg >= 20) c = 20;   // W = 13, top window 14 bits
+  else if (lg >= 17) c = 17;   // W = 15, top window 16 bits
+  else if (lg >= 14) c = 15;   // W = 17, top window 14 bits
+  else c = 13;                 // W = 20, top window 7 bits
   if (c < 10) c = 10;
   if (c > 23) c = 23;
   const unsigned W = (255 + c - 1) / c;
@@ -593,8 +630,8 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
                                                 chunk_idx);
     B200ZK_LAUNCH_CHECK(ctx, "msm_big_list_kernel");
     const size_t shm = BIG_THREADS * sizeof(G1XYZZ);
-    msm_big_accumulate_kernel<<<ctx->sm_count * 2, BIG_THREADS, shm, st>>>(base_ptr, starts, sorted, plan, chunk_bucket,
-                                                                         chunk_idx, ctx->msm_big.p);
+    msm_big_accumulate_kernel<<<ctx->sm_count * 4, BIG_THREADS, 0, st>>>(base_ptr, starts, sorted, plan, chunk_bucket,
+                                                                       chunk_idx, ctx->msm_big.p);
     B200ZK_LAUNCH_CHECK(ctx, "msm_big_accumulate_kernel");
     msm_big_reduce_kernel<<<ctx->sm_count, BIG_THREADS, shm, st>>>(starts, plan, big_bucket, big_first, big_cap,
                                                                    ctx->msm_big.p, ctx->msm_buckets.p);
