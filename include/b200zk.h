@@ -74,6 +74,19 @@ int b200zk_ntt_dev(b200zk_ctx* ctx, void* a_dev, unsigned log2n, int inverse, in
  * Same inverse / coset semantics as b200zk_ntt (scalings are applied in the half that owns the first / last stage). */
 int b200zk_ntt_dist_half_dev(b200zk_ctx* ctx, const void* src_dev, void* dst_dev, unsigned log2n, unsigned log2g,
                              unsigned rank, unsigned log2c, int half, int inverse, int decimation, int coset);
+/* Fused variant of half 0: the last pass stores every element straight into the destination rank's exchange buffer
+ * through peer-mapped pointers (NVLink stores, tile by tile, overlapping the butterflies) instead of writing locally and
+ * calling an all-to-all.  peer_bufs[k] = rank k's exchange buffer of 2^(log2n-log2g) elements as seen from THIS process
+ * (own buffer for k == rank, b200zk_ipc_import'ed pointers otherwise); g <= 8.  After it (and a cross-rank barrier)
+ * every rank's buffer holds what all_to_all_single would have delivered: Z for DIF, X for DIT.  src is clobbered. */
+int b200zk_ntt_dist_half0_p2p_dev(b200zk_ctx* ctx, void* src_dev, void* const* peer_bufs, unsigned log2n, unsigned log2g,
+                                  unsigned rank, unsigned log2c, int inverse, int decimation, int coset);
+/* device buffers that can be shared with the other ranks' processes (CUDA IPC) */
+int b200zk_dev_alloc(b200zk_ctx* ctx, size_t bytes, void** out);
+int b200zk_dev_free(b200zk_ctx* ctx, void* p);
+int b200zk_ipc_export(b200zk_ctx* ctx, void* dev_ptr, void* handle_out_64);
+int b200zk_ipc_import(b200zk_ctx* ctx, const void* handle_64, void** out);
+int b200zk_ipc_close(b200zk_ctx* ctx, void* imported);
 /* tests / tuning: force the plain radix-2 pass kernel instead of the radix-4 register kernel (same results) */
 int b200zk_ntt_set_radix2(b200zk_ctx* ctx, int on);
 /* fft.BitReverse(a): in-place index bit-reversal permutation. */

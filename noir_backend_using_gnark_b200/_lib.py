@@ -54,6 +54,12 @@ def load() -> C.CDLL:
         "b200zk_ntt_dev": (i, [vp, vp, u, i, i, i]),
         "b200zk_ntt_dist_half_dev": (i, [vp, vp, vp, u, u, u, u, i, i, i, i]),
         "b200zk_ntt_set_radix2": (i, [vp, i]),
+        "b200zk_ntt_dist_half0_p2p_dev": (i, [vp, vp, C.POINTER(vp), u, u, u, u, i, i, i]),
+        "b200zk_dev_alloc": (i, [vp, sz, C.POINTER(vp)]),
+        "b200zk_dev_free": (i, [vp, vp]),
+        "b200zk_ipc_export": (i, [vp, vp, vp]),
+        "b200zk_ipc_import": (i, [vp, vp, C.POINTER(vp)]),
+        "b200zk_ipc_close": (i, [vp, vp]),
         "b200zk_bit_reverse": (i, [vp, vp, u]),
         "b200zk_bit_reverse_dev": (i, [vp, vp, u]),
         "b200zk_bases_upload": (i, [vp, vp, sz, C.POINTER(vp)]),

@@ -136,6 +136,53 @@ int b200zk_ntt_dist_half_dev(b200zk_ctx* ctx, const void* src_dev, void* dst_dev
   return ntt_dist_run(ctx, src_dev, dst_dev, log2n, log2g, rank, log2c, half, inverse != 0, decimation, coset != 0);
 }
 
+int b200zk_ntt_dist_half0_p2p_dev(b200zk_ctx* ctx, void* src_dev, void* const* peer_bufs, unsigned log2n, unsigned log2g,
+                                  unsigned rank, unsigned log2c, int inverse, int decimation, int coset) {
+  B200ZK_TRY(enter(ctx));
+  if (!src_dev || !peer_bufs || (decimation != B200ZK_DIF && decimation != B200ZK_DIT)) return B200ZK_ERR_BAD_ARG;
+  // the local destination is unused by the scattering pass; pass src so in-place passes before it work on src
+  return ntt_dist_run(ctx, src_dev, src_dev, log2n, log2g, rank, log2c, 0, inverse != 0, decimation, coset != 0, peer_bufs);
+}
+
+int b200zk_dev_alloc(b200zk_ctx* ctx, size_t bytes, void** out) {
+  B200ZK_TRY(enter(ctx));
+  if (!out || !bytes) return B200ZK_ERR_BAD_ARG;
+  B200ZK_CUDA(ctx, cudaMalloc(out, bytes));
+  return B200ZK_OK;
+}
+
+int b200zk_dev_free(b200zk_ctx* ctx, void* p) {
+  B200ZK_TRY(enter(ctx));
+  B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  B200ZK_CUDA(ctx, cudaFree(p));
+  return B200ZK_OK;
+}
+
+int b200zk_ipc_export(b200zk_ctx* ctx, void* dev_ptr, void* handle_out_64) {
+  B200ZK_TRY(enter(ctx));
+  if (!dev_ptr || !handle_out_64) return B200ZK_ERR_BAD_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  cudaIpcMemHandle_t h;
+  B200ZK_CUDA(ctx, cudaIpcGetMemHandle(&h, dev_ptr));
+  memcpy(handle_out_64, &h, 64);
+  return B200ZK_OK;
+}
+
+int b200zk_ipc_import(b200zk_ctx* ctx, const void* handle_64, void** out) {
+  B200ZK_TRY(enter(ctx));
+  if (!handle_64 || !out) return B200ZK_ERR_BAD_ARG;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle_64, 64);
+  B200ZK_CUDA(ctx, cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+  return B200ZK_OK;
+}
+
+int b200zk_ipc_close(b200zk_ctx* ctx, void* imported) {
+  B200ZK_TRY(enter(ctx));
+  B200ZK_CUDA(ctx, cudaIpcCloseMemHandle(imported));
+  return B200ZK_OK;
+}
+
 int b200zk_bit_reverse_dev(b200zk_ctx* ctx, void* a_dev, unsigned log2n) {
   B200ZK_TRY(enter(ctx));
   if (!a_dev || log2n > B200ZK_MAX_LOG2N) return B200ZK_ERR_BAD_ARG;

@@ -145,7 +145,7 @@ struct PhaseTimer {
 // entry points implemented in ntt.cu / msm.cu
 int ntt_run(b200zk_ctx* ctx, void* a_dev, unsigned log2n, int inverse, int decimation, int coset);
 int ntt_dist_run(b200zk_ctx* ctx, const void* src, void* dst, unsigned log2n, unsigned log2g, unsigned rank,
-                 unsigned log2c, int half, int inverse, int decimation, int coset);
+                 unsigned log2c, int half, int inverse, int decimation, int coset, void* const* peers = nullptr);
 int bit_reverse_run(b200zk_ctx* ctx, void* a_dev, unsigned log2n);
 void ntt_free_domains(b200zk_ctx* ctx);
 int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const void* scalars_dev, size_t n,

@@ -146,7 +146,18 @@ struct PassParams {
   const uint4* lo;
   const uint4* hi;
   const uint4* ninv;
+  // fused four-step exchange: the tile is stored straight into the peers' exchange buffers over NVLink (peer-mapped
+  // pointers, one per rank) instead of into `dst`; destination rank = top bits of the (permuted) local address
+  unsigned peer_on, peer_chunk_log, peer_rank;
+  uint4* peer_dst[8];
 };
+
+__device__ __forceinline__ uint4* store_target(const PassParams& p, uint4* dst, size_t addr) {
+  if (!p.peer_on) return dst + 2 * addr;
+  const size_t peer = addr >> p.peer_chunk_log;
+  const size_t off = ((size_t)p.peer_rank << p.peer_chunk_log) | (addr & (((size_t)1 << p.peer_chunk_log) - 1));
+  return p.peer_dst[peer] + 2 * off;
+}
 
 __device__ __forceinline__ size_t tile_to_local(const PassParams& p, size_t tile, unsigned r, unsigned c) {
   const unsigned Lc = p.L < p.cb ? p.L : p.cb;
@@ -259,7 +270,7 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(const uint4* __restrict__
     if (p.scale == SCALE_POST_NINV) v = fe_mul(v, fe_load_ro<FrParams>(p.ninv));
     if (p.scale == SCALE_POST_COSET) v = fe_mul(v, coset_factor(p, local_to_logical(p, l)));
     const size_t addr = p.dst_perm ? permuted(p, l) : l;
-    fe_store(dst + 2 * addr, v);
+    fe_store(store_target(p, dst, addr), v);
   }
 }
 
@@ -411,7 +422,7 @@ __global__ void __launch_bounds__(256, 3) ntt_pass4_kernel(const uint4* __restri
         if (p.scale == SCALE_POST_NINV) v = fe_mul(v, fe_load_ro<FrParams>(p.ninv));
         if (p.scale == SCALE_POST_COSET) v = fe_mul(v, coset_factor(p, local_to_logical(p, l)));
         const size_t addr = p.dst_perm ? permuted(p, l) : l;
-        fe_store(dst + 2 * addr, v);
+        fe_store(store_target(p, dst, addr), v);
       }
     }
   }
@@ -449,6 +460,8 @@ struct NttSlice {
   unsigned perm_a, perm_b;
   bool src_perm, dst_perm;
   bool first, last;                       // slice contains the first / last executed stage of the whole transform
+  void* const* peers = nullptr;           // when set: the last pass scatters into these peer buffers (fused exchange)
+  unsigned npeers = 0;
 };
 
 // Runs the stages of `sl` on src -> dst (src == dst allowed when no permutation is requested).
@@ -467,7 +480,7 @@ static int run_slice(b200zk_ctx* ctx, const void* src, void* dst, const NttSlice
     unsigned base = nstages / npass, rem = nstages % npass;
     for (unsigned i = 0; i < npass; i++) ks[i] = base + (i < rem ? 1 : 0);
   }
-  if ((sl.src_perm || sl.dst_perm) && src == dst) return B200ZK_ERR_BAD_ARG;
+  if ((sl.src_perm || sl.dst_perm) && src == dst && !sl.peers) return B200ZK_ERR_BAD_ARG;
   unsigned done = 0;
   for (unsigned pi = 0; pi < npass; pi++) {
     PassParams p;
@@ -485,6 +498,15 @@ static int run_slice(b200zk_ctx* ctx, const void* src, void* dst, const NttSlice
     p.src_perm = (sl.src_perm && pi == 0) ? 1 : 0;
     p.dst_perm = (sl.dst_perm && pi == npass - 1) ? 1 : 0;
     p.tw = (const uint4*)(inverse ? d.tw_inv : d.tw_fwd);
+    p.peer_on = 0;
+    p.peer_chunk_log = p.peer_rank = 0;
+    for (int i = 0; i < 8; i++) p.peer_dst[i] = nullptr;
+    if (sl.peers && pi == npass - 1) {
+      p.peer_on = 1;
+      p.peer_chunk_log = sl.nl - sl.gap_bits;
+      p.peer_rank = sl.gap_val;
+      for (unsigned i = 0; i < sl.npeers && i < 8; i++) p.peer_dst[i] = (uint4*)sl.peers[i];
+    }
     p.lo = p.hi = nullptr;
     p.ninv = (const uint4*)d.scalars;
     p.scale = SCALE_NONE;
@@ -561,7 +583,7 @@ int ntt_run(b200zk_ctx* ctx, void* a_dev, unsigned log2n, int inverse, int decim
 //   DIT: half 0 = strides < C on the row-block shard, last pass writes the block layout to dst; exchange;
 //        half 1 = strides >= C on the column-block shard (in place).
 int ntt_dist_run(b200zk_ctx* ctx, const void* src, void* dst, unsigned log2n, unsigned log2g, unsigned rank,
-                 unsigned log2c, int half, int inverse, int decimation, int coset) {
+                 unsigned log2c, int half, int inverse, int decimation, int coset, void* const* peers) {
   if (log2n > B200ZK_MAX_LOG2N || log2g == 0 || log2c < log2g + MIN_CB || log2n < log2c + log2g || rank >> log2g)
     return B200ZK_ERR_BAD_ARG;
   B200ZK_TRY(build_domain(ctx, log2n));
@@ -590,6 +612,11 @@ int ntt_dist_run(b200zk_ctx* ctx, const void* src, void* dst, unsigned log2n, un
   }
   sl.first = half == 0;
   sl.last = half == 1;
+  if (peers) {
+    if (half != 0 || log2g > 3) return B200ZK_ERR_BAD_ARG;
+    sl.peers = peers;
+    sl.npeers = 1u << log2g;
+  }
   return run_slice(ctx, src, dst, sl, inverse, dit, coset);
 }
 

@@ -76,7 +76,7 @@ class DistributedDomain:
     """fft.NewDomain(2^log2n) sharded over the ranks of a torch.distributed process group."""
 
     def __init__(self, m: int, ctx=None, group=None, log2c: Optional[int] = None,
-                 half_fn: Optional[Callable] = None):
+                 half_fn: Optional[Callable] = None, p2p: bool = False):
         import torch.distributed as dist
 
         self.dist = dist
@@ -91,6 +91,79 @@ class DistributedDomain:
         self.ctx = ctx
         self._half_fn = half_fn or self._device_half
         self._scratch = None
+        self.p2p = bool(p2p)
+        self._peer_ptrs = None
+        if self.p2p:
+            self._setup_p2p()
+
+    # -- fused exchange: peer-mapped exchange buffers (CUDA IPC), one per rank ------------------------
+    def _setup_p2p(self) -> None:
+        import ctypes as C
+
+        import torch
+
+        assert self.world <= 8, "the fused exchange addresses at most 8 peers"
+        lib, h = self.ctx.lib, self.ctx.handle
+        nbytes = self.layout.local * 32
+        own = C.c_void_p()
+        _lib.check(h, lib.b200zk_dev_alloc(h, nbytes, C.byref(own)))
+        self._own_buf = own
+        handle = (C.c_ubyte * 64)()
+        _lib.check(h, lib.b200zk_ipc_export(h, own, handle))
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device="cuda:%d" % self.ctx.device)
+        allh = [torch.zeros_like(mine) for _ in range(self.world)]
+        self.dist.all_gather(allh, mine, group=self.group)
+        ptrs = (C.c_void_p * self.world)()
+        self._imported = []
+        for k in range(self.world):
+            if k == self.rank:
+                ptrs[k] = own.value
+            else:
+                raw = (C.c_ubyte * 64)(*allh[k].cpu().tolist())
+                out = C.c_void_p()
+                _lib.check(h, lib.b200zk_ipc_import(h, raw, C.byref(out)))
+                ptrs[k] = out.value
+                self._imported.append(out)
+        self._peer_ptrs = ptrs
+
+        class _View:  # zero-copy torch view of the library-owned exchange buffer
+            __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (own.value, False), "version": 2}
+
+        self._exchange = torch.as_tensor(_View(), device="cuda:%d" % self.ctx.device)
+        self._flag = torch.zeros(1, dtype=torch.int32, device="cuda:%d" % self.ctx.device)
+
+    def _stream_barrier(self) -> None:
+        """cross-rank barrier in stream order (a 4-byte all-reduce on the library's stream)"""
+        import torch
+
+        with torch.cuda.stream(self.ctx.torch_stream()):
+            self.dist.all_reduce(self._flag, group=self.group)
+
+    def _run_p2p(self, x, inverse: int, decimation: int, coset: int):
+        lay = self.layout
+        lib, h = self.ctx.lib, self.ctx.handle
+        self._stream_barrier()   # every rank is done with its exchange buffer from the previous transform
+        rc = lib.b200zk_ntt_dist_half0_p2p_dev(h, x.data_ptr(), self._peer_ptrs, lay.log2n, lay.log2g, self.rank,
+                                               lay.log2c, inverse, decimation, coset)
+        _lib.check(h, rc)
+        self._stream_barrier()   # all peers' stores have landed
+        ex = self._exchange
+        if decimation == DIF:
+            self._device_half(ex, x, 1, inverse, decimation, coset)   # reads Z from the exchange buffer, writes Y
+            return x
+        self._device_half(ex, ex, 1, inverse, decimation, coset)      # in place on X
+        return ex
+
+    def close(self) -> None:
+        if self._peer_ptrs is not None:
+            lib, h = self.ctx.lib, self.ctx.handle
+            self.ctx.sync()
+            self.dist.barrier(group=self.group)
+            for p in self._imported:
+                lib.b200zk_ipc_close(h, p)
+            self.dist.barrier(group=self.group)
+            lib.b200zk_dev_free(h, self._own_buf)
+            self._peer_ptrs = None
 
     # -- local halves (libb200zk.so) ---------------------------------------------------------------
     def _device_half(self, src, dst, half: int, inverse: int, decimation: int, coset: int) -> None:
@@ -122,6 +195,8 @@ class DistributedDomain:
     def _run(self, x, inverse: int, decimation: int, coset: bool):
         assert x.numel() * x.element_size() == self.layout.local * 32
         coset = int(bool(coset))
+        if self.p2p:
+            return self._run_p2p(x, inverse, decimation, coset)
         tmp = self._buffer_like(x)
         if decimation == DIF:
             self._half_fn(x, x, 0, inverse, decimation, coset)       # strides >= C, column-block, in place
@@ -134,8 +209,9 @@ class DistributedDomain:
         return x
 
     def FFT(self, x, decimation: int, coset: bool = False):
-        """Sharded domain.FFT.  x: this rank's shard (column-block for DIF, row-block for DIT), transformed in
-        place; the result shard is row-block for DIF and column-block for DIT."""
+        """Sharded domain.FFT.  x: this rank's shard (column-block for DIF, row-block for DIT); returns the tensor
+        holding the result shard (row-block for DIF, column-block for DIT) — x itself, or with p2p=True and DIT the
+        domain's exchange buffer (valid until the next transform).  x is clobbered either way."""
         return self._run(x, 0, decimation, coset)
 
     def FFTInverse(self, x, decimation: int, coset: bool = False):
