@@ -147,6 +147,11 @@ int b200zk_msm_set_window(b200zk_ctx* ctx, int c);
  *   BatchedProof.ClaimedValues[0..6] and ZShiftedOpening.ClaimedValue as fr.Element (32 B each).
  * Must be called with the context the key was set up on. */
 typedef struct b200zk_plonk_pk b200zk_plonk_pk;
+/* Commitment hook: when set, every kzg.Commit inside b200zk_plonk_prove calls fn(user, scalars_dev, n, out_dev)
+ * instead of the local MSM.  fn must leave the canonical affine commitment (64 B) at out_dev, ordered on the context
+ * stream (b200zk_stream).  Used to shard the prover's MSMs over the GPUs of one box (dist_prove.py). */
+typedef int (*b200zk_commit_fn)(void* user, const void* scalars_dev, size_t n, void* out_affine_dev);
+int b200zk_plonk_set_commit_hook(b200zk_plonk_pk* pk, b200zk_commit_fn fn, void* user);
 int b200zk_plonk_setup(b200zk_ctx* ctx, const b200zk_bases* bases, unsigned log2n, unsigned log2n_big,
                        unsigned nb_public, unsigned nb_wires, const void* ql_l, const void* qr_l, const void* qm_l,
                        const void* qo_l, const void* qk_l, const int64_t* permutation, const uint32_t* lro,

@@ -76,6 +76,7 @@ def load() -> C.CDLL:
         "b200zk_plonk_setup": (i, [vp, vp, u, u, u, u, vp, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]),
         "b200zk_plonk_pk_free": (None, [vp, vp]),
         "b200zk_plonk_vk": (i, [vp, vp, vp]),
+        "b200zk_plonk_set_commit_hook": (i, [vp, vp, vp]),
         "b200zk_plonk_pk_poly": (i, [vp, vp, i, vp]),
         "b200zk_plonk_prove": (i, [vp, vp, vp, vp, vp]),
         "b200zk_microbench": (i, [vp, i, C.POINTER(C.c_double)]),

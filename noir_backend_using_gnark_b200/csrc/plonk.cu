@@ -458,6 +458,9 @@ struct b200zk_plonk_pk {
   uint4 *lin, *folded_h, *folded, *quot, *chunks, *partials, *scal;
   void* points;       // 16 x 64 B result slots
   uint8_t vk_points[8 * 64];  // S0,S1,S2,Ql,Qr,Qm,Qo,Qk affine (Montgomery)
+  // optional replacement for the local MSM of every commitment (multi-GPU: point-range-sharded MSM + NVLink gather)
+  b200zk_commit_fn commit_hook = nullptr;
+  void* commit_user = nullptr;
 };
 
 namespace {
@@ -512,7 +515,12 @@ int to_coset(b200zk_ctx* ctx, const uint4* canonical, size_t len, uint4* out, un
 }
 
 int commit(b200zk_ctx* ctx, const b200zk_plonk_pk* pk, const uint4* poly, size_t len, int slot) {
-  return msm_run(ctx, pk->bases, 0, poly, len, (char*)pk->points + 64 * slot, 0);
+  void* out = (char*)pk->points + 64 * slot;
+  if (pk->commit_hook) {
+    int rc = pk->commit_hook(pk->commit_user, poly, len, out);
+    return rc == 0 ? B200ZK_OK : (rc < 0 ? rc : B200ZK_ERR_CUDA);
+  }
+  return msm_run(ctx, pk->bases, 0, poly, len, out, 0);
 }
 
 int fetch_points(b200zk_ctx* ctx, const b200zk_plonk_pk* pk, int first, int count, uint8_t* out) {
@@ -682,6 +690,13 @@ void b200zk_plonk_pk_free(b200zk_ctx* ctx, b200zk_plonk_pk* pk) {
   }
   if (pk->arena) cudaFree(pk->arena);
   delete pk;
+}
+
+int b200zk_plonk_set_commit_hook(b200zk_plonk_pk* pk, b200zk_commit_fn fn, void* user) {
+  if (!pk) return B200ZK_ERR_BAD_ARG;
+  pk->commit_hook = fn;
+  pk->commit_user = user;
+  return B200ZK_OK;
 }
 
 int b200zk_plonk_vk(b200zk_ctx* ctx, const b200zk_plonk_pk* pk, void* out_8_points) {
