@@ -189,34 +189,60 @@ def run_reference(args, rank: int, world: int) -> None:
 # ------------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------------
-def run_prove(ctx, log2n: int) -> dict:
+def run_prove(ctx, log2n: int, rank: int = 0, world: int = 1):
     """BASELINE metric 1: full PLONK prove latency (device-resident prover, b200zk_plonk_prove) on the synthetic
-    chain circuit of 2^log2n - 1 gates + 1 public input; the proof is checked by the independent verifier."""
+    chain circuit of 2^log2n - 1 gates + 1 public input; the proof is checked by the independent verifier.
+    With world > 1 the prover's commitments are sharded by point range over the ranks (dist_prove.py): rank 0
+    proves, the other ranks serve MSM shards; both the single-GPU and the sharded latency are reported."""
     import numpy as np
 
     import noir_backend_using_gnark_b200 as zk
     from noir_backend_using_gnark_b200 import plonk as zkp
 
     sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    n = 1 << log2n
+    a_int = SEED_SRS * 0x9E3779B97F4A7C15 % zkp.R_MOD
+    a_img = zkp.fr_to_mont([a_int])
+    com = None
+    if world > 1:
+        from noir_backend_using_gnark_b200.dist_prove import ShardedCommitter
+
+        m = -(-(n + 3) // world)
+        shard = zk.SRS.NewSRS(m, a_img, ctx, first=rank * m).precompute()
+        com = ShardedCommitter(ctx, shard, m)
+        if rank != 0:
+            com.serve()
+            shard.close()
+            return None
     from prove_bench import synthetic
 
-    n = 1 << log2n
     c = synthetic(log2n)
-    a_int = SEED_SRS * 0x9E3779B97F4A7C15 % zkp.R_MOD
-    srs = zk.SRS.NewSRS(n + 3, zkp.fr_to_mont([a_int]), ctx).precompute()
+    srs = zk.SRS.NewSRS(n + 3, a_img, ctx).precompute()
     t0 = time.perf_counter()
     pk = zkp.ProvingKey.SetupRaw(srs, log2n, log2n + 2, 1, c["nb_wires"], c["ql"], c["qr"], c["qm"], c["qo"], c["qk"],
                                  c["lro"], ctx)
     setup_ms = (time.perf_counter() - t0) * 1e3
     blind = random_fr_images(9, 0xB2000006)
-    pk.Prove(c["sol"], blind)  # warm-up
-    times = []
-    l0 = ctx.launch_count
-    for _ in range(3):
-        t0 = time.perf_counter()
-        proof = pk.Prove(c["sol"], blind)
-        times.append((time.perf_counter() - t0) * 1e3)
-    launches = (ctx.launch_count - l0) // 3
+
+    def timed():
+        pk.Prove(c["sol"], blind)  # warm-up
+        ts = []
+        l0 = ctx.launch_count
+        for _ in range(3):
+            t0 = time.perf_counter()
+            pr = pk.Prove(c["sol"], blind)
+            ts.append((time.perf_counter() - t0) * 1e3)
+        return pr, ts, (ctx.launch_count - l0) // 3
+
+    proof, times, launches = timed()
+    sharded = None
+    if com is not None:
+        com.attach(pk)
+        proof_s, times_s, _ = timed()
+        com.stop()
+        com.detach(pk)
+        sharded = {"gpus": world, "ms": min(times_s), "ms_all": times_s, "same_proof_bytes": proof_s.blob == proof.blob,
+                   "error": repr(com.error) if com.error else None}
     # acceptance by the independent verifier (checker only: oracle/plonk.py pairing check)
     from oracle import bn254 as o
     from oracle import plonk as pl
@@ -229,7 +255,7 @@ def run_prove(ctx, log2n: int) -> dict:
     return {"metric": "plonk_prove_latency", "log2_gates": log2n, "ms": min(times), "ms_all": times, "unit": "ms",
             "higher_is_better": False, "setup_ms": setup_ms, "launches_per_prove": int(launches), "verified": ok,
             "api": "b200zk_plonk_prove (host solution vector in, 832-byte proof out; H2D/D2H included)",
-            "h2d_bytes": n * 32 + 288, "d2h_bytes": 832}
+            "h2d_bytes": n * 32 + 288, "d2h_bytes": 832, "sharded_msm": sharded}
 
 
 def run_b200(args, rank: int, world: int, local_rank: int) -> None:
@@ -335,6 +361,17 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
     e2e_s = float(t.item())
     assert res_host == res_dev, "host-API and device-API MSM results differ"
 
+    # ---- PLONK prove (all ranks take part when world > 1: the commitments are sharded)
+    prove_info = None
+    cpu_pts = None
+    if rank == 0 and not args.no_cpu:
+        cpu_pts = np.frombuffer(srs.download(0, 1 << min(CPU_SAMPLE_LOG2, log2n)), dtype=np.uint8)
+    if not args.no_prove:
+        srs.close()          # free the 2^24 window table before the prover allocates its arena
+        del d_sc
+        torch.cuda.empty_cache()
+        prove_info = run_prove(ctx, args.prove_log2n, rank, world)
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -374,14 +411,10 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
                     "passes": -(-nlog // 8) if nlog > 10 else 1}
         del a
 
-    prove_info = None
-    if not args.no_prove:
-        prove_info = run_prove(ctx, args.prove_log2n)
-
     cpu = None
     if not args.no_cpu:
         ns = 1 << min(CPU_SAMPLE_LOG2, log2n)
-        pts = np.frombuffer(srs.download(0, ns), dtype=np.uint8)  # cpu_baseline leg: the only oracle use in this arm
+        pts = cpu_pts  # first 2^20 SRS points, downloaded above; this leg is the only oracle compute in this arm
         dt, cores = cpu_msm_sample(pts, h_sc.numpy()[: ns * 32], ns, reps=1)
         cpu = {"value": ns / dt / 1e6, "unit": "Mpoints/s", "cores": cores, "kind": "port",
                "sample": "first 2^%d points of the same MSM, C restatement of gnark-crypto MultiExp on all host cores "

@@ -478,19 +478,22 @@ static void g1x_to_affine(g1a* r, const g1x* p) {
 
 /* ---------------------------------------------------------------------------------------------- MSM */
 typedef struct {
-  const g1a* pts; const int32_t* digits; size_t n; unsigned c, W; g1x* wsum;
+  const g1a* pts; const int32_t* digits; size_t n; unsigned c, W, S; g1x* wsum;
 } msm_arg;
 
-/* processChunk: one window -> sum_b b * bucket[b] */
+/* processChunk: one (point segment, window) task -> sum_b b * bucket[b].  gnark splits the point range when it has
+ * more tasks (2*NumCPU) than windows and adds the sub-results (multiexp.go: nbSplits); S segments here. */
 static void msm_window_range(void* p, size_t lo, size_t hi, int tid) {
   (void)tid;
   msm_arg* m = (msm_arg*)p;
   size_t B = (size_t)1 << (m->c - 1);
   g1x* buckets = (g1x*)malloc(sizeof(g1x) * B);
-  for (size_t w = lo; w < hi; w++) {
+  for (size_t t = lo; t < hi; t++) {
+    const size_t seg = t / m->W, w = t % m->W;
+    const size_t i_lo = m->n * seg / m->S, i_hi = m->n * (seg + 1) / m->S;
     for (size_t b = 0; b < B; b++) g1x_set_inf(&buckets[b]);
     const int32_t* dg = m->digits + w * m->n;
-    for (size_t i = 0; i < m->n; i++) {
+    for (size_t i = i_lo; i < i_hi; i++) {
       int32_t d = dg[i];
       if (d == 0) continue;
       if (d > 0) g1x_add_mixed(&buckets[d - 1], &m->pts[i], 0);
@@ -503,7 +506,7 @@ static void msm_window_range(void* p, size_t lo, size_t hi, int tid) {
       g1x_add(&run, &buckets[b]);
       g1x_add(&tot, &run);
     }
-    m->wsum[w] = tot;
+    m->wsum[t] = tot;
   }
   free(buckets);
 }
@@ -548,13 +551,22 @@ int oracle_msm(const void* points, const void* scalars, size_t n, void* out, int
       digits[(size_t)w * n + i] = d;
     }
   }
-  g1x* wsum = (g1x*)malloc(sizeof(g1x) * W);
-  msm_arg m = {pts, digits, n, c, W, wsum};
-  parallel_for(W, nthreads < 1 ? 1 : nthreads, msm_window_range, &m);
-  g1x tot = wsum[W - 1];
-  for (int w = (int)W - 2; w >= 0; w--) {
-    for (unsigned k = 0; k < c; k++) g1x_double(&tot);
-    g1x_add(&tot, &wsum[w]);
+  if (nthreads < 1) nthreads = 1;
+  unsigned S = (unsigned)nthreads / W;
+  if (S < 1) S = 1;
+  if ((size_t)S > n) S = (unsigned)n;
+  g1x* wsum = (g1x*)malloc(sizeof(g1x) * W * S);
+  msm_arg m = {pts, digits, n, c, W, S, wsum};
+  parallel_for((size_t)W * S, nthreads, msm_window_range, &m);
+  g1x tot;
+  g1x_set_inf(&tot);
+  for (unsigned seg = 0; seg < S; seg++) {
+    g1x part = wsum[seg * W + W - 1];
+    for (int w = (int)W - 2; w >= 0; w--) {
+      for (unsigned k = 0; k < c; k++) g1x_double(&part);
+      g1x_add(&part, &wsum[seg * W + w]);
+    }
+    g1x_add(&tot, &part);
   }
   g1x_to_affine((g1a*)out, &tot);
   free(wsum);
