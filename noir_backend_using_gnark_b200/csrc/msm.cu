@@ -134,7 +134,7 @@ __device__ __forceinline__ G1Affine load_signed(const void* bases, unsigned entr
 
 // Threads take buckets in order of decreasing run length (`order`), so the 32 runs of a warp have (almost) the same
 // length and the longest runs start first: no lane idles while its neighbours finish.
-__global__ void __launch_bounds__(128) msm_accumulate_kernel(const void* __restrict__ bases, const unsigned* __restrict__ starts,
+__global__ void __launch_bounds__(128, 4) msm_accumulate_kernel(const void* __restrict__ bases, const unsigned* __restrict__ starts,
                                                              const unsigned* __restrict__ sorted,
                                                              const unsigned* __restrict__ order, MsmShape sh,
                                                              unsigned nbuckets, void* __restrict__ buckets) {
