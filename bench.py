@@ -63,7 +63,7 @@ def load_peaks() -> dict:
 
 
 class ClockSampler:
-    """Samples SM clocks and throttle reasons during the timed region (NVML, 100 ms period)."""
+    """Samples SM clocks and throttle reasons during the timed region (NVML, 20 ms period)."""
 
     def __init__(self, index: int):
         self.index = index
@@ -100,7 +100,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.02)
 
     def start(self):
         if self.nv is None:

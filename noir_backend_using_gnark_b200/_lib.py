@@ -35,10 +35,16 @@ def load() -> C.CDLL:
     if _lib is not None:
         return _lib
     if not LIB_PATH.exists():
-        raise ImportError(
-            "%s is missing: build it with `python -m noir_backend_using_gnark_b200.build` "
-            "(this package has no CPU fallback)" % LIB_PATH
-        )
+        # not a fallback: the same CUDA library, compiled on the spot when the prebuilt .so did not travel
+        try:
+            from . import build as _build
+
+            _build.build()
+        except Exception as e:
+            raise ImportError(
+                "%s is missing and could not be built (%s): run `python -m noir_backend_using_gnark_b200.build` "
+                "(this package has no CPU fallback)" % (LIB_PATH, e)
+            )
     lib = C.CDLL(str(LIB_PATH))
     vp, sz, u, i = C.c_void_p, C.c_size_t, C.c_uint, C.c_int
     sig = {

@@ -206,3 +206,32 @@ def test_precomputed_window_table(ctx, log2n, c):
     eq = np.tile(np.frombuffer(o.fr_to_mont_bytes([v]), dtype=np.uint8), n)
     assert zk.MultiExp(srs, eq) == cref.msm(pts, eq, n, nthreads=cref.ncores())
     srs.close()
+
+
+def test_full_size_2_24_table_vs_classic_vs_shards(ctx):
+    """BASELINE size (2^24 points): no oracle at this size — the window-table path, the classic path and the
+    two-shard combination must agree byte for byte (three different summation orders of the same MSM)."""
+    import torch
+
+    n = 1 << 24
+    alpha = o.fr_to_mont_bytes([o.random_fr(1, 0xB2000005)[0]])
+    srs = zk.SRS.NewSRS(n, alpha, ctx)
+    sc = torch.from_numpy(cref.random_fr(n, 0xB2000001)).cuda()
+    torch.cuda.synchronize()
+    out = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    zk.MultiExp(srs, sc, n=n, out=out)
+    ctx.sync()
+    classic = out.cpu().numpy().tobytes()
+    srs.precompute()
+    zk.MultiExp(srs, sc, n=n, out=out)
+    ctx.sync()
+    table = out.cpu().numpy().tobytes()
+    half = n // 2
+    parts = torch.empty(256, dtype=torch.uint8, device="cuda")
+    zk.MultiExp(srs, sc[: half * 32], n=half, first_base=0, out=parts[:128], partial=True)
+    zk.MultiExp(srs, sc[half * 32:], n=half, first_base=half, out=parts[128:], partial=True)
+    res = zk.SumPartials(ctx, parts)
+    ctx.sync()
+    assert classic == table == res.cpu().numpy().tobytes()
+    assert classic != b"\0" * 64
+    srs.close()

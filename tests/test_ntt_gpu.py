@@ -189,3 +189,26 @@ def test_radix2_and_radix4_kernels_agree(ctx):
                 lib.b200zk_ntt_set_radix2(ctx.handle, r2)
                 assert run_gpu(ctx, a, log2n, inv, dec, cos).tobytes() == want, (log2n, inv, dec, cos, r2)
     lib.b200zk_ntt_set_radix2(ctx.handle, 0)
+
+
+def test_large_sizes_roundtrip(ctx):
+    """2^25 and 2^26 (4 passes): FFTInverse(FFT(x)) == x, coset, both decimations (size-independent property)."""
+    import torch
+
+    for log2n in (25, 26):
+        n = 1 << log2n
+        x = torch.from_numpy(cref.random_fr(n, 0xB2000003 + log2n)).cuda()
+        d = zk.Domain(n, ctx)
+        y = x.clone()
+        torch.cuda.synchronize()
+        d.FFT(y, zk.DIF, True)
+        d.FFTInverse(y, zk.DIT, True)
+        ctx.sync()
+        assert torch.equal(y, x)
+        d.FFTInverse(y, zk.DIF, False)
+        zk.BitReverse(y, ctx)
+        d.FFT(y, zk.DIF, False)
+        zk.BitReverse(y, ctx)
+        ctx.sync()
+        assert torch.equal(y, x)
+        del x, y

@@ -95,3 +95,23 @@ def test_large_circuit_verifies(ctx):
     assert pl.verify(pl.Proof.from_bytes(proof.to_gnark_bytes()), vk, x[:1], g2)
     pk_d.close()
     srs_d.close()
+
+
+def test_plonk_api_rejects_bad_arguments(ctx):
+    import ctypes as C
+
+    lib = zk.load()
+    h = C.c_void_p()
+    srs = zk.SRS.NewSRS(16, o.fr_to_mont_bytes([ALPHA]), ctx)
+    buf = np.zeros(64 * 32, dtype=np.uint8)
+    perm = np.zeros(3 * 8, dtype=np.int64)
+    lro = np.zeros(3 * 8, dtype=np.uint32)
+    args = (buf.ctypes.data,) * 5 + (perm.ctypes.data, lro.ctypes.data)
+    # SRS too small for n = 2^4 (needs n + 3 points)
+    assert lib.b200zk_plonk_setup(ctx.handle, srs.handle, 4, 6, 1, 4, *args, C.byref(h)) == -3
+    # big domain must be at least 4n
+    assert lib.b200zk_plonk_setup(ctx.handle, srs.handle, 3, 4, 1, 4, *args, C.byref(h)) == -3
+    assert lib.b200zk_plonk_setup(ctx.handle, None, 3, 5, 1, 4, *args, C.byref(h)) == -3
+    assert lib.b200zk_plonk_prove(ctx.handle, None, buf.ctypes.data, buf.ctypes.data, buf.ctypes.data) == -3
+    assert lib.b200zk_plonk_vk(ctx.handle, None, buf.ctypes.data) == -3
+    srs.close()
