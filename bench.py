@@ -198,7 +198,49 @@ def run_reference(args, rank: int, world: int) -> None:
 # ------------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------------
-def run_prove(ctx, log2n: int, rank: int = 0, world: int = 1):
+def prove_cpu_baseline(ctx, sample_log2: int) -> dict:
+    """CPU arm of the prove metric on a bounded sample: the C port of the prover (oracle/bn254_ref.c, all host
+    cores) on a 2^sample_log2-row chain circuit, next to the CUDA prover on the SAME circuit, SRS and blinding —
+    whose proof bytes must be identical (three-way parity: Python oracle == C port == CUDA is covered by the tests)."""
+    import numpy as np
+
+    import noir_backend_using_gnark_b200 as zk
+    from noir_backend_using_gnark_b200 import plonk as zkp
+    from oracle import bn254 as o
+    from oracle import cref
+    from oracle import plonk as pl
+
+    gates = (1 << sample_log2) - 1
+    cs_o, x = pl.synthetic_chain_circuit(gates, 0xB2000004)
+    alpha = SEED_SRS * 0x9E3779B97F4A7C15 % zkp.R_MOD
+    srs_o = pl.SRS((1 << sample_log2) + 3, alpha)
+    pk_o = pl.setup(cs_o, srs_o)
+    cp = pl.CProver(cs_o, pk_o, srs_o)
+    blind = random_fr_images(9, 0xB2000006).tobytes()
+    sol = np.frombuffer(o.fr_to_mont_bytes(x), dtype=np.uint8).copy()
+    cores = cref.ncores()
+    t0 = time.perf_counter()
+    blob_cpu = cp.prove_blob(sol, blind, cores)
+    cpu_ms = (time.perf_counter() - t0) * 1e3
+    g = cs_o.gates
+    cs_p = zkp.SparseR1CS(cs_o.nb_public, cs_o.nb_secret, [t.ql for t in g], [t.qr for t in g], [t.qm for t in g],
+                          [t.qo for t in g], [t.qk for t in g], [t.a for t in g], [t.b for t in g], [t.c for t in g])
+    srs_d = zk.SRS.NewSRS((1 << sample_log2) + 3, zkp.fr_to_mont([alpha]), ctx).precompute()
+    pk_d = zkp.ProvingKey.Setup(cs_p, srs_d, ctx)
+    pk_d.Prove(sol, blind)
+    t0 = time.perf_counter()
+    proof_gpu = pk_d.Prove(sol, blind)
+    gpu_ms = (time.perf_counter() - t0) * 1e3
+    same = proof_gpu.blob == blob_cpu
+    pk_d.close()
+    srs_d.close()
+    return {"value": cpu_ms, "unit": "ms", "cores": cores, "kind": "port",
+            "sample": "full PLONK prove of a 2^%d-row chain circuit by the C port of the prover (not gnark: no Go "
+                      "toolchain here)" % sample_log2,
+            "b200_ms_same_circuit": gpu_ms, "proof_bytes_identical_to_cpu_port": bool(same)}
+
+
+def run_prove(ctx, log2n: int, rank: int = 0, world: int = 1, cpu_sample_log2: int = 0):
     """BASELINE metric 1: full PLONK prove latency (device-resident prover, b200zk_plonk_prove) on the synthetic
     chain circuit of 2^log2n - 1 gates + 1 public input; the proof is checked by the independent verifier.
     With world > 1 the prover's commitments are sharded by point range over the ranks (dist_prove.py): rank 0
@@ -261,7 +303,9 @@ def run_prove(ctx, log2n: int, rank: int = 0, world: int = 1):
     ok = bool(pl.verify(pl.Proof.from_bytes(proof.to_gnark_bytes()), vk, [c["x0"]], (pl.G2_GEN, pl.g2_mul(pl.G2_GEN, a_int))))
     pk.close()
     srs.close()
+    cpu = prove_cpu_baseline(ctx, cpu_sample_log2) if cpu_sample_log2 else None
     return {"metric": "plonk_prove_latency", "log2_gates": log2n, "ms": min(times), "ms_all": times, "unit": "ms",
+            "cpu_baseline": cpu,
             "higher_is_better": False, "setup_ms": setup_ms, "launches_per_prove": int(launches), "verified": ok,
             "api": "b200zk_plonk_prove (host solution vector in, 832-byte proof out; H2D/D2H included)",
             "h2d_bytes": n * 32 + 288, "d2h_bytes": 832, "sharded_msm": sharded}
@@ -379,7 +423,7 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
         srs.close()          # free the 2^24 window table before the prover allocates its arena
         del d_sc
         torch.cuda.empty_cache()
-        prove_info = run_prove(ctx, args.prove_log2n, rank, world)
+        prove_info = run_prove(ctx, args.prove_log2n, rank, world, 0 if args.no_cpu else 16)
 
     if rank != 0:
         if world > 1:

@@ -666,3 +666,340 @@ void oracle_g1_mul_gen_batch(const void* scalars, size_t n, void* out, int nthre
   mulgen_arg m = {(const fe*)scalars, (g1a*)out};
   parallel_for(n, nthreads < 1 ? 1 : nthreads, mulgen_range, &m);
 }
+
+/* ============================================================================================================
+ * PLONK prover, C restatement (gnark v0.8.0 backend/plonk/bn254 Prove as called at
+ * /root/reference/gnark_backend_ffi/backend/plonk/plonk.go:67; same steps as oracle/plonk.py prove(), which is the
+ * readable statement of the algorithm — this port exists to give the CPU baseline of the prove metric a compiled,
+ * multi-threaded arm and a third implementation for the byte-parity tests).  Parity status: unpinned vs real gnark.
+ * ============================================================================================================ */
+typedef struct { uint32_t h[8]; uint8_t buf[64]; uint64_t len; size_t fill; } sha256_ctx;
+static const uint32_t SHA_K[64] = {
+    0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98,
+    0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786,
+    0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8,
+    0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967, 0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13,
+    0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85, 0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819,
+    0xd6990624, 0xf40e3585, 0x106aa070, 0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a,
+    0x5b9cca4f, 0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7,
+    0xc67178f2};
+static uint32_t rotr32(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+static void sha_block(sha256_ctx* s, const uint8_t* p) {
+  uint32_t w[64];
+  for (int i = 0; i < 16; i++) w[i] = ((uint32_t)p[4*i] << 24) | ((uint32_t)p[4*i+1] << 16) | ((uint32_t)p[4*i+2] << 8) | p[4*i+3];
+  for (int i = 16; i < 64; i++) {
+    uint32_t s0 = rotr32(w[i-15], 7) ^ rotr32(w[i-15], 18) ^ (w[i-15] >> 3);
+    uint32_t s1 = rotr32(w[i-2], 17) ^ rotr32(w[i-2], 19) ^ (w[i-2] >> 10);
+    w[i] = w[i-16] + s0 + w[i-7] + s1;
+  }
+  uint32_t a = s->h[0], b = s->h[1], c = s->h[2], d = s->h[3], e = s->h[4], f = s->h[5], g = s->h[6], h = s->h[7];
+  for (int i = 0; i < 64; i++) {
+    uint32_t t1 = h + (rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25)) + ((e & f) ^ (~e & g)) + SHA_K[i] + w[i];
+    uint32_t t2 = (rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
+    h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+  }
+  s->h[0] += a; s->h[1] += b; s->h[2] += c; s->h[3] += d; s->h[4] += e; s->h[5] += f; s->h[6] += g; s->h[7] += h;
+}
+static void sha_init(sha256_ctx* s) {
+  static const uint32_t iv[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+  memcpy(s->h, iv, sizeof(iv)); s->len = 0; s->fill = 0;
+}
+static void sha_update(sha256_ctx* s, const void* data, size_t n) {
+  const uint8_t* p = (const uint8_t*)data;
+  s->len += n;
+  while (n) {
+    size_t take = 64 - s->fill < n ? 64 - s->fill : n;
+    memcpy(s->buf + s->fill, p, take);
+    s->fill += take; p += take; n -= take;
+    if (s->fill == 64) { sha_block(s, s->buf); s->fill = 0; }
+  }
+}
+static void sha_final(sha256_ctx* s, uint8_t out[32]) {
+  uint64_t bits = s->len * 8;
+  uint8_t pad = 0x80, z = 0, lb[8];
+  sha_update(s, &pad, 1);
+  while (s->fill != 56) sha_update(s, &z, 1);
+  for (int i = 0; i < 8; i++) lb[i] = (uint8_t)(bits >> (56 - 8 * i));
+  sha_update(s, lb, 8);
+  for (int i = 0; i < 8; i++) { out[4*i] = s->h[i] >> 24; out[4*i+1] = s->h[i] >> 16; out[4*i+2] = s->h[i] >> 8; out[4*i+3] = s->h[i]; }
+}
+
+static void fe_marshal(const field* F, const fe* a_mont, uint8_t out[32]) {
+  fe r; fe_from_mont(F, &r, a_mont);
+  for (int i = 0; i < 4; i++) for (int b = 0; b < 8; b++) out[31 - (8*i + b)] = (uint8_t)(r.l[i] >> (8*b));
+}
+static void g1_marshal(const g1a* p, uint8_t out[64]) {
+  if (g1a_is_inf(p)) { memset(out, 0, 64); out[0] = 0x40; return; }
+  fe_marshal(&FP, &p->x, out); fe_marshal(&FP, &p->y, out + 32);
+}
+static void fr_set_bytes(fe* r, const uint8_t in[32]) {
+  fe v;
+  for (int i = 0; i < 4; i++) { uint64_t w = 0; for (int b = 0; b < 8; b++) w |= (uint64_t)in[31 - (8*i + b)] << (8*b); v.l[i] = w; }
+  while (fe_geq(v.l, FR.m)) raw_sub(v.l, v.l, FR.m);
+  fe_to_mont(&FR, r, &v);
+}
+typedef struct { sha256_ctx s; int have_prev; uint8_t prev[32]; } transcript;
+static void tr_begin(transcript* t, const char* name) { sha_init(&t->s); sha_update(&t->s, name, strlen(name)); if (t->have_prev) sha_update(&t->s, t->prev, 32); }
+static void tr_point(transcript* t, const g1a* p) { uint8_t b[64]; g1_marshal(p, b); sha_update(&t->s, b, 64); }
+static void tr_fr(transcript* t, const fe* v) { uint8_t b[32]; fe_marshal(&FR, v, b); sha_update(&t->s, b, 32); }
+static void tr_finish(transcript* t, fe* out) { sha_final(&t->s, t->prev); t->have_prev = 1; fr_set_bytes(out, t->prev); }
+
+#define FMUL(r, a, b) fe_mul(&FR, (r), (a), (b))
+#define FADD(r, a, b) fe_add(&FR, (r), (a), (b))
+#define FSUB(r, a, b) fe_sub(&FR, (r), (a), (b))
+
+static void fr_pow_u64(fe* r, const fe* a, uint64_t e) {
+  fe acc = FR.one, base = *a;
+  while (e) { if (e & 1) FMUL(&acc, &acc, &base); FMUL(&base, &base, &base); e >>= 1; }
+  *r = acc;
+}
+static void poly_eval(fe* r, const fe* p, size_t len, const fe* z) {
+  fe acc; memset(&acc, 0, 32);
+  for (size_t i = len; i-- > 0;) { FMUL(&acc, &acc, z); FADD(&acc, &acc, &p[i]); }
+  *r = acc;
+}
+/* q = (f - f(a)) / (X - a); len(q) = len - 1 */
+static void poly_div_x_minus_a(fe* q, const fe* f, size_t len, const fe* a) {
+  fe g; memset(&g, 0, 32);
+  for (size_t i = len; i-- > 1;) { FMUL(&g, &g, a); FADD(&g, &g, &f[i]); q[i - 1] = g; }
+}
+static void to_canonical(fe* a, unsigned log2n, int nthreads) {
+  oracle_ntt(a, log2n, 1, 0, 0, nthreads);
+  oracle_bit_reverse(a, log2n);
+}
+static void to_coset(fe* out, const fe* canonical, size_t len, unsigned log_big, int nthreads) {
+  size_t N = (size_t)1 << log_big;
+  memcpy(out, canonical, len * 32);
+  memset(out + len, 0, (N - len) * 32);
+  oracle_ntt(out, log_big, 0, 0, 1, nthreads);
+}
+
+typedef struct {
+  unsigned log2n, log_big;
+  const fe *el, *er, *eo, *ez, *eqk, *ql, *qr, *qm, *qo, *s1, *s2, *s3, *lone;
+  const fe* tw_big;
+  fe alpha, beta, gamma, beta_u, beta_uu, u;
+  fe xn_inv[8];
+  fe* out;
+} quot_arg;
+static void quot_range(void* p, size_t lo, size_t hi, int tid) {
+  (void)tid;
+  quot_arg* q = (quot_arg*)p;
+  const size_t N = (size_t)1 << q->log_big, ratio = N >> q->log2n;
+  for (size_t i = lo; i < hi; i++) {
+    size_t nat = bitrev(i, q->log_big);
+    size_t ishift = bitrev((nat + ratio) & (N - 1), q->log_big);
+    const fe *L = &q->el[i], *R = &q->er[i], *O = &q->eo[i];
+    fe ic, t, x, a, b, Lg, Rg, Og, one_t, c;
+    FMUL(&ic, &q->ql[i], L);
+    FMUL(&t, &q->qr[i], R); FADD(&ic, &ic, &t);
+    FMUL(&t, &q->qm[i], L); FMUL(&t, &t, R); FADD(&ic, &ic, &t);
+    FMUL(&t, &q->qo[i], O); FADD(&ic, &ic, &t);
+    FADD(&ic, &ic, &q->eqk[i]);
+    if (nat < N / 2) x = q->tw_big[nat]; else fe_neg(&FR, &x, &q->tw_big[nat - N / 2]);
+    FMUL(&x, &x, &q->u);
+    FADD(&Lg, L, &q->gamma); FADD(&Rg, R, &q->gamma); FADD(&Og, O, &q->gamma);
+    FMUL(&t, &q->beta, &x); FADD(&a, &Lg, &t);
+    FMUL(&t, &q->beta_u, &x); FADD(&t, &Rg, &t); FMUL(&a, &a, &t);
+    FMUL(&t, &q->beta_uu, &x); FADD(&t, &Og, &t); FMUL(&a, &a, &t);
+    FMUL(&a, &a, &q->ez[i]);
+    FMUL(&t, &q->beta, &q->s1[i]); FADD(&b, &Lg, &t);
+    FMUL(&t, &q->beta, &q->s2[i]); FADD(&t, &Rg, &t); FMUL(&b, &b, &t);
+    FMUL(&t, &q->beta, &q->s3[i]); FADD(&t, &Og, &t); FMUL(&b, &b, &t);
+    FMUL(&b, &b, &q->ez[ishift]);
+    FSUB(&b, &b, &a);
+    FSUB(&one_t, &q->ez[i], &FR.one); FMUL(&one_t, &one_t, &q->lone[i]);
+    FMUL(&c, &one_t, &q->alpha); FADD(&c, &c, &b);
+    FMUL(&c, &c, &q->alpha); FADD(&c, &c, &ic);
+    FMUL(&q->out[i], &c, &q->xn_inv[nat & (ratio - 1)]);
+  }
+}
+
+typedef struct { const fe *l, *r, *o; const int64_t* perm; const fe* ident; fe beta, gamma; size_t n; fe *num, *den; } zterm_arg;
+static void zterm_range(void* p, size_t lo, size_t hi, int tid) {
+  (void)tid;
+  zterm_arg* z = (zterm_arg*)p;
+  const fe* w[3] = {z->l, z->r, z->o};
+  for (size_t j = lo; j < hi; j++) {
+    fe a = FR.one, b = FR.one, t, wg;
+    for (int k = 0; k < 3; k++) {
+      FADD(&wg, &w[k][j], &z->gamma);
+      FMUL(&t, &z->beta, &z->ident[k * z->n + j]); FADD(&t, &wg, &t); FMUL(&a, &a, &t);
+      FMUL(&t, &z->beta, &z->ident[z->perm[k * z->n + j]]); FADD(&t, &wg, &t); FMUL(&b, &b, &t);
+    }
+    z->num[j] = a; z->den[j] = b;
+  }
+}
+
+/* Inputs are gnark in-memory images (Montgomery).  pk polynomials: canonical ql,qr,qm,qo,cqk,s1,s2,s3 and Lagrange lqk
+ * (n each); coset forms of ql,qr,qm,qo,s1,s2,s3 and L_1 on the big domain (bit-reversed layout, N4 each) as gnark
+ * keeps them in the loaded key.  proof_out: same 832-byte layout as b200zk_plonk_prove. */
+int oracle_plonk_prove(unsigned log2n, unsigned log_big, unsigned nb_public, unsigned nb_wires, const void* polys_n[9],
+                       const void* cosets_big[8], const int64_t* perm, const uint32_t* lro, const void* vk_points,
+                       const void* srs_g1, const void* solution, const void* blinding, int nthreads, void* proof_out) {
+  const size_t n = (size_t)1 << log2n, N4 = (size_t)1 << log_big, m = n + 2;
+  (void)nb_wires;
+  const fe *ql = polys_n[0], *qr = polys_n[1], *qm = polys_n[2], *qo = polys_n[3], *cqk = polys_n[4], *lqk = polys_n[5],
+           *s1 = polys_n[6], *s2 = polys_n[7], *s3 = polys_n[8];
+  const fe* sol = (const fe*)solution;
+  const fe* bl = (const fe*)blinding;
+  const g1a* vk = (const g1a*)vk_points;
+  domain* dn = get_domain(log2n);
+  domain* db = get_domain(log_big);
+  fe *l = malloc(n * 32), *r = malloc(n * 32), *o = malloc(n * 32);
+  fe *cl = calloc(n + 8, 32), *cr = calloc(n + 8, 32), *co = calloc(n + 8, 32), *cz = calloc(n + 8, 32), *qk = malloc(n * 32);
+  for (size_t i = 0; i < n; i++) { l[i] = sol[lro[i]]; r[i] = sol[lro[n + i]]; o[i] = sol[lro[2 * n + i]]; }
+  fe* lag[3] = {l, r, o};
+  fe* can[3] = {cl, cr, co};
+  g1a pts[11]; /* LRO[3], Z, H[3], batched H, zshift H, lin digest, folded digest */
+  for (int k = 0; k < 3; k++) {
+    memcpy(can[k], lag[k], n * 32);
+    to_canonical(can[k], log2n, nthreads);
+    for (int i = 0; i < 2; i++) { FSUB(&can[k][i], &can[k][i], &bl[2 * k + i]); FADD(&can[k][n + i], &can[k][n + i], &bl[2 * k + i]); }
+    oracle_msm(srs_g1, can[k], n + 2, &pts[k], nthreads, 0);
+  }
+  transcript fs; fs.have_prev = 0;
+  fe gamma, beta, alpha, zeta;
+  tr_begin(&fs, "gamma");
+  for (int i = 0; i < 8; i++) tr_point(&fs, &vk[i]);
+  for (unsigned i = 0; i < nb_public; i++) tr_fr(&fs, &sol[i]);
+  for (int i = 0; i < 3; i++) tr_point(&fs, &pts[i]);
+  tr_finish(&fs, &gamma);
+  tr_begin(&fs, "beta"); tr_finish(&fs, &beta);
+  /* identity support [w^i | u w^i | u^2 w^i] */
+  fe* ident = malloc(3 * n * 32);
+  fe u; fe_set_u64(&FR, &u, 5);
+  fe uu; FMUL(&uu, &u, &u);
+  for (size_t i = 0; i < n; i++) {
+    fe w;
+    if (i < n / 2 || n == 1) w = dn->tw[i < n / 2 ? i : 0]; else fe_neg(&FR, &w, &dn->tw[i - n / 2]);
+    ident[i] = w; FMUL(&ident[n + i], &w, &u); FMUL(&ident[2 * n + i], &w, &uu);
+  }
+  fe *num = malloc(n * 32), *den = malloc(n * 32), *pre = malloc(n * 32);
+  zterm_arg za = {l, r, o, perm, ident, beta, gamma, n, num, den};
+  parallel_for(n, nthreads, zterm_range, &za);
+  { /* batch inversion of den (Montgomery's trick), then z = exclusive prefix product of num/den */
+    fe acc = FR.one;
+    for (size_t i = 0; i < n; i++) { pre[i] = acc; FMUL(&acc, &acc, &den[i]); }
+    fe inv; fe_inv(&FR, &inv, &acc);
+    for (size_t i = n; i-- > 0;) { fe di; FMUL(&di, &inv, &pre[i]); FMUL(&inv, &inv, &den[i]); FMUL(&num[i], &num[i], &di); }
+    acc = FR.one;
+    for (size_t i = 0; i < n; i++) { cz[i] = acc; FMUL(&acc, &acc, &num[i]); }
+  }
+  to_canonical(cz, log2n, nthreads);
+  for (int i = 0; i < 3; i++) { FSUB(&cz[i], &cz[i], &bl[6 + i]); FADD(&cz[n + i], &cz[n + i], &bl[6 + i]); }
+  oracle_msm(srs_g1, cz, n + 3, &pts[3], nthreads, 0);
+  tr_begin(&fs, "alpha"); tr_point(&fs, &pts[3]); tr_finish(&fs, &alpha);
+  memcpy(qk, lqk, n * 32);
+  for (unsigned i = 0; i < nb_public; i++) qk[i] = sol[i];
+  to_canonical(qk, log2n, nthreads);
+  fe *el = malloc(N4 * 32), *er = malloc(N4 * 32), *eo = malloc(N4 * 32), *ez = malloc(N4 * 32), *eqk = malloc(N4 * 32), *t = malloc(N4 * 32);
+  to_coset(el, cl, n + 2, log_big, nthreads); to_coset(er, cr, n + 2, log_big, nthreads); to_coset(eo, co, n + 2, log_big, nthreads);
+  to_coset(ez, cz, n + 3, log_big, nthreads); to_coset(eqk, qk, n, log_big, nthreads);
+  quot_arg qa;
+  qa.log2n = log2n; qa.log_big = log_big;
+  qa.el = el; qa.er = er; qa.eo = eo; qa.ez = ez; qa.eqk = eqk;
+  qa.ql = cosets_big[0]; qa.qr = cosets_big[1]; qa.qm = cosets_big[2]; qa.qo = cosets_big[3];
+  qa.s1 = cosets_big[4]; qa.s2 = cosets_big[5]; qa.s3 = cosets_big[6]; qa.lone = cosets_big[7];
+  qa.tw_big = db->tw; qa.alpha = alpha; qa.beta = beta; qa.gamma = gamma; qa.u = u;
+  FMUL(&qa.beta_u, &beta, &u); FMUL(&qa.beta_uu, &qa.beta_u, &u);
+  {
+    fe un, w, wi = FR.one, v;
+    fr_pow_u64(&un, &u, (uint64_t)n);
+    fr_pow_u64(&w, &db->tw[N4 >= 2 ? 1 : 0], (uint64_t)n); /* w_{4n}^n */
+    size_t ratio = N4 >> log2n;
+    for (size_t i = 0; i < 8; i++) {
+      if (i < ratio) { FMUL(&v, &un, &wi); FSUB(&v, &v, &FR.one); fe_inv(&FR, &qa.xn_inv[i], &v); FMUL(&wi, &wi, &w); }
+      else qa.xn_inv[i] = FR.one;
+    }
+  }
+  qa.out = t;
+  parallel_for(N4, nthreads, quot_range, &qa);
+  oracle_ntt(t, log_big, 1, 1, 1, nthreads); /* FFTInverse(DIT, coset): bit-reversed Lagrange-coset -> canonical */
+  for (int k = 0; k < 3; k++) oracle_msm(srs_g1, t + k * m, m, &pts[4 + k], nthreads, 0);
+  tr_begin(&fs, "zeta"); for (int i = 0; i < 3; i++) tr_point(&fs, &pts[4 + i]); tr_finish(&fs, &zeta);
+  fe lz, rz, oz, s1z, s2z, zu, zeta_shift, omega;
+  if (n >= 4) omega = dn->tw[1];
+  else if (n == 2) fe_neg(&FR, &omega, &FR.one);
+  else omega = FR.one;
+  FMUL(&zeta_shift, &zeta, &omega);
+  poly_eval(&lz, cl, n + 2, &zeta); poly_eval(&rz, cr, n + 2, &zeta); poly_eval(&oz, co, n + 2, &zeta);
+  poly_eval(&s1z, s1, n, &zeta); poly_eval(&s2z, s2, n, &zeta); poly_eval(&zu, cz, n + 3, &zeta_shift);
+  fe* quot = malloc((n + 8) * 32);
+  poly_div_x_minus_a(quot, cz, n + 3, &zeta_shift);
+  oracle_msm(srs_g1, quot, n + 2, &pts[8], nthreads, 0);
+  /* linearised polynomial */
+  fe c1, c2, lagv, rl, tt, t2, uz, uuz;
+  FMUL(&c1, &s1z, &beta); FADD(&c1, &c1, &lz); FADD(&c1, &c1, &gamma);
+  FMUL(&tt, &s2z, &beta); FADD(&tt, &tt, &rz); FADD(&tt, &tt, &gamma);
+  FMUL(&c1, &c1, &tt); FMUL(&c1, &c1, &zu); FMUL(&c1, &c1, &beta);
+  FMUL(&uz, &zeta, &u); FMUL(&uuz, &uz, &u);
+  FMUL(&c2, &beta, &zeta); FADD(&c2, &c2, &lz); FADD(&c2, &c2, &gamma);
+  FMUL(&tt, &beta, &uz); FADD(&tt, &tt, &rz); FADD(&tt, &tt, &gamma); FMUL(&c2, &c2, &tt);
+  FMUL(&tt, &beta, &uuz); FADD(&tt, &tt, &oz); FADD(&tt, &tt, &gamma); FMUL(&c2, &c2, &tt);
+  fe_neg(&FR, &c2, &c2);
+  fr_pow_u64(&lagv, &zeta, (uint64_t)n); FSUB(&lagv, &lagv, &FR.one);
+  FSUB(&tt, &zeta, &FR.one); fe_inv(&FR, &t2, &tt); FMUL(&lagv, &lagv, &t2);
+  FMUL(&lagv, &lagv, &alpha); FMUL(&lagv, &lagv, &alpha); FMUL(&lagv, &lagv, &dn->ninv);
+  FMUL(&rl, &rz, &lz);
+  fe* lin = malloc((n + 8) * 32);
+  for (size_t i = 0; i < n + 3; i++) {
+    fe v, w;
+    FMUL(&v, &cz[i], &c2);
+    if (i < n) { FMUL(&w, &s3[i], &c1); FADD(&v, &v, &w); }
+    FMUL(&v, &v, &alpha);
+    if (i < n) {
+      FMUL(&w, &qm[i], &rl); FADD(&v, &v, &w);
+      FMUL(&w, &ql[i], &lz); FADD(&v, &v, &w);
+      FMUL(&w, &qr[i], &rz); FADD(&v, &v, &w);
+      FMUL(&w, &qo[i], &oz); FADD(&v, &v, &w);
+      FADD(&v, &v, &cqk[i]);
+    }
+    FMUL(&w, &cz[i], &lagv); FADD(&lin[i], &v, &w);
+  }
+  oracle_msm(srs_g1, lin, n + 3, &pts[9], nthreads, 0);
+  /* folded H */
+  fe zpm; fr_pow_u64(&zpm, &zeta, (uint64_t)m);
+  fe* fh = malloc((n + 8) * 32);
+  for (size_t i = 0; i < m; i++) {
+    fe v; FMUL(&v, &t[2 * m + i], &zpm); FADD(&v, &v, &t[m + i]); FMUL(&v, &v, &zpm); FADD(&fh[i], &v, &t[i]);
+  }
+  { /* folded digest = H0 + zpm*(H1 + zpm*H2) by double-and-add */
+    fe zr; fe_from_mont(&FR, &zr, &zpm);
+    g1x acc; g1x_set_inf(&acc); g1x_add_mixed(&acc, &pts[6], 0);
+    for (int k = 1; k >= 0; k--) {
+      g1a base; g1x_to_affine(&base, &acc);
+      g1x_set_inf(&acc);
+      for (int b = 255; b >= 0; b--) { g1x_double(&acc); if ((zr.l[b / 64] >> (b % 64)) & 1) g1x_add_mixed(&acc, &base, 0); }
+      g1x_add_mixed(&acc, &pts[4 + k], 0);
+    }
+    g1x_to_affine(&pts[10], &acc);
+  }
+  fe claimed[7];
+  poly_eval(&claimed[0], fh, m, &zeta); poly_eval(&claimed[1], lin, n + 3, &zeta);
+  claimed[2] = lz; claimed[3] = rz; claimed[4] = oz; claimed[5] = s1z; claimed[6] = s2z;
+  transcript kz; kz.have_prev = 0;
+  fe gk;
+  tr_begin(&kz, "gamma"); tr_fr(&kz, &zeta);
+  tr_point(&kz, &pts[10]); tr_point(&kz, &pts[9]);
+  for (int i = 0; i < 3; i++) tr_point(&kz, &pts[i]);
+  tr_point(&kz, &vk[0]); tr_point(&kz, &vk[1]);
+  tr_finish(&kz, &gk);
+  const fe* polys[7] = {fh, lin, cl, cr, co, s1, s2};
+  const size_t lens[7] = {m, n + 3, n + 2, n + 2, n + 2, n, n};
+  fe* folded = calloc(n + 8, 32);
+  fe gp = FR.one;
+  for (int k = 0; k < 7; k++) {
+    for (size_t j = 0; j < lens[k]; j++) { fe v; FMUL(&v, &polys[k][j], &gp); FADD(&folded[j], &folded[j], &v); }
+    FMUL(&gp, &gp, &gk);
+  }
+  poly_div_x_minus_a(quot, folded, n + 3, &zeta);
+  oracle_msm(srs_g1, quot, n + 2, &pts[7], nthreads, 0);
+  uint8_t* out = (uint8_t*)proof_out;
+  memcpy(out, pts, 9 * 64);
+  memcpy(out + 576, claimed, 7 * 32);
+  memcpy(out + 576 + 224, &zu, 32);
+  free(l); free(r); free(o); free(cl); free(cr); free(co); free(cz); free(qk); free(ident); free(num); free(den); free(pre);
+  free(el); free(er); free(eo); free(ez); free(eqk); free(t); free(quot); free(lin); free(fh); free(folded);
+  return 0;
+}

@@ -39,6 +39,8 @@ def load() -> C.CDLL:
         lib.oracle_g1_add_affine.argtypes = [vp, vp, vp]
         lib.oracle_random_fr.argtypes = [vp, sz, C.c_uint64]
         lib.oracle_g1_mul_gen_batch.argtypes = [vp, sz, vp, i]
+        lib.oracle_plonk_prove.restype = i
+        lib.oracle_plonk_prove.argtypes = [u, u, u, u, C.POINTER(vp), C.POINTER(vp), vp, vp, vp, vp, vp, vp, i, vp]
         for name in ("oracle_fr_mul", "oracle_fp_mul", "oracle_fr_add", "oracle_fr_sub"):
             getattr(lib, name).argtypes = [vp, vp, vp]
         for name in ("oracle_fr_inv", "oracle_fp_inv"):

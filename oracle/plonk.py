@@ -879,3 +879,53 @@ def synthetic_chain_circuit(nb_gates: int, seed: int, nb_public: int = 1):
 
 
 REFERENCE_FIXTURES = None  # filled lazily from /root/reference in tests/golden/make_golden.py, not at run time
+
+
+# ======================================================================================================
+# 7. the same prover through the C port (oracle/bn254_ref.c: oracle_plonk_prove) — CPU baseline + third opinion
+# ======================================================================================================
+class CProver:
+    """Prepares the loaded-key arrays once (what gnark holds after ProvingKey.ReadFrom) and proves through C."""
+
+    def __init__(self, cs: SparseR1CS, pk: ProvingKey, srs: SRS):
+        import ctypes as C
+
+        self.C = C
+        self.lib = cref.load()
+        self.cs, self.pk, self.srs = cs, pk, srs
+        n, N4 = pk.n, pk.n_big
+        dom = o.Domain(n)
+        lone = to_lagrange_coset_bitrev([pow(n, -1, R)] * n, N4)     # L_1 = (1/n) sum X^i on the coset
+        arr = lambda v: np.frombuffer(o.fr_to_mont_bytes(v), dtype=np.uint8).copy()
+        self.polys = [arr(x) for x in (pk.ql, pk.qr, pk.qm, pk.qo, pk.cqk, pk.lqk, pk.s1, pk.s2, pk.s3)]
+        self.cosets = [arr(x) for x in (pk.l_ql, pk.l_qr, pk.l_qm, pk.l_qo, pk.l_s1, pk.l_s2, pk.l_s3, lone)]
+        self.perm = np.asarray(pk.permutation, dtype=np.int64)
+        self.lro = np.asarray(pk.lro_wires, dtype=np.uint32)
+        vk = pk.vk
+        self.vk_points = np.frombuffer(o.g1_to_bytes(vk.S + [vk.Ql, vk.Qr, vk.Qm, vk.Qo, vk.Qk]), dtype=np.uint8).copy()
+        del dom
+
+    def prove_blob(self, full_witness, blinding_images: bytes, nthreads: int = 0) -> bytes:
+        C = self.C
+        sol = np.frombuffer(o.fr_to_mont_bytes(full_witness), dtype=np.uint8).copy() if not isinstance(full_witness, np.ndarray) else full_witness
+        bl = np.frombuffer(bytes(blinding_images), dtype=np.uint8).copy()
+        out = np.zeros(832, dtype=np.uint8)
+        P = (C.c_void_p * 9)(*[a.ctypes.data for a in self.polys])
+        Q = (C.c_void_p * 8)(*[a.ctypes.data for a in self.cosets])
+        n = self.pk.n
+        rc = self.lib.oracle_plonk_prove(n.bit_length() - 1, self.pk.n_big.bit_length() - 1, self.cs.nb_public,
+                                         self.cs.nb_public + self.cs.nb_secret, P, Q, self.perm.ctypes.data,
+                                         self.lro.ctypes.data, self.vk_points.ctypes.data, self.srs.g1_bytes.ctypes.data,
+                                         sol.ctypes.data, bl.ctypes.data, nthreads or cref.ncores(), out.ctypes.data)
+        assert rc == 0
+        return out.tobytes()
+
+    def prove(self, full_witness, blinding_images: bytes, nthreads: int = 0) -> Proof:
+        return proof_from_blob(self.prove_blob(full_witness, blinding_images, nthreads))
+
+
+def proof_from_blob(blob: bytes) -> Proof:
+    """832-byte in-memory proof image (9 G1Affine + 8 fr.Element) -> Proof"""
+    pts = o.g1_from_bytes(blob[:576])
+    vals = o.fr_from_mont_bytes(blob[576:])
+    return Proof(pts[0:3], pts[3], pts[4:7], pts[7], vals[:7], pts[8], vals[7])

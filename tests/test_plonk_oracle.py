@@ -107,3 +107,20 @@ def test_vectorised_permutation_matches_gnark_cycle_walk():
             if perm[i] == -1:
                 perm[i] = cycle[lro[i]]
         assert got.tolist() == perm
+
+
+@pytest.mark.parametrize("gates,nb_public", [(1, 1), (13, 1), (300, 3)])
+def test_c_prover_matches_python_prover(gates, nb_public):
+    """third implementation: the C port (CPU baseline arm) must emit the same proof bytes as the Python oracle"""
+    cs, x = pl.synthetic_chain_circuit(gates, 0xB2000004 + gates, nb_public)
+    size = 1
+    while size < gates + nb_public:
+        size <<= 1
+    srs = pl.SRS(size + 3, 0xB2000005)
+    pk = pl.setup(cs, srs)
+    want = pl.prove(cs, pk, srs, x, pl.BlindingStream(11)).to_bytes()
+    st = pl.BlindingStream(11)
+    blind = b"".join(o.limbs_le(st.next_mont()) for _ in range(9))
+    got = pl.CProver(cs, pk, srs).prove(x, blind, nthreads=3)
+    assert got.to_bytes() == want
+    assert pl.verify(got, pk.vk, x[:nb_public], srs.g2)
