@@ -156,6 +156,15 @@ int b200zk_plonk_setup(b200zk_ctx* ctx, const b200zk_bases* bases, unsigned log2
                        unsigned nb_public, unsigned nb_wires, const void* ql_l, const void* qr_l, const void* qm_l,
                        const void* qo_l, const void* qk_l, const int64_t* permutation, const uint32_t* lro,
                        b200zk_plonk_pk** out);
+/* plonk.Setup(spr, srs) straight from the SparseR1CS the reference builds
+ * (/root/reference/gnark_backend_ffi/backend/plonk/sparse_r1cs.go:98-106): one entry per constraint
+ * qL*xa + qR*xb + qO*xc + qM*(xa*xb) + qC == 0 — coefficient columns (Montgomery fr, qm = coeff(M[0])*coeff(M[1]))
+ * and the wire ids of L, R, O (public wires are 0..nb_public-1, secret wires follow).  Row layout, padding and gnark's
+ * buildPermutation are done inside (host, O(n)). */
+int b200zk_plonk_setup_r1cs(b200zk_ctx* ctx, const b200zk_bases* bases, unsigned nb_public, unsigned nb_secret,
+                            size_t nb_constraints, const void* ql, const void* qr, const void* qm, const void* qo,
+                            const void* qk, const uint32_t* wire_a, const uint32_t* wire_b, const uint32_t* wire_c,
+                            b200zk_plonk_pk** out);
 void b200zk_plonk_pk_free(b200zk_ctx* ctx, b200zk_plonk_pk* pk);
 int b200zk_plonk_vk(b200zk_ctx* ctx, const b200zk_plonk_pk* pk, void* out_8_points);
 /* copy a key polynomial to the host (n fr): which = 0..8 -> Ql,Qr,Qm,Qo,CQk (canonical), LQk (Lagrange), S1,S2,S3 */

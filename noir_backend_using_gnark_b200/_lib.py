@@ -80,6 +80,7 @@ def load() -> C.CDLL:
         "b200zk_g1_sum_dev": (i, [vp, vp, sz, vp]),
         "b200zk_msm_set_window": (i, [vp, i]),
         "b200zk_plonk_setup": (i, [vp, vp, u, u, u, u, vp, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]),
+        "b200zk_plonk_setup_r1cs": (i, [vp, vp, u, u, sz, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]),
         "b200zk_plonk_pk_free": (None, [vp, vp]),
         "b200zk_plonk_vk": (i, [vp, vp, vp]),
         "b200zk_plonk_set_commit_hook": (i, [vp, vp, vp]),

@@ -682,6 +682,51 @@ int b200zk_plonk_setup(b200zk_ctx* ctx, const b200zk_bases* bases, unsigned log2
   return B200ZK_OK;
 }
 
+// plonk.Setup(spr, srs) from the constraint system itself: lays out the rows [placeholders | constraints | padding],
+// the wire columns and gnark's permutation (buildPermutation: every position points to the previous position holding
+// the same wire, the first occurrence to the last) on the host, then runs b200zk_plonk_setup.
+int b200zk_plonk_setup_r1cs(b200zk_ctx* ctx, const b200zk_bases* bases, unsigned nb_public, unsigned nb_secret,
+                            size_t nb_constraints, const void* ql, const void* qr, const void* qm, const void* qo,
+                            const void* qk, const uint32_t* wire_a, const uint32_t* wire_b, const uint32_t* wire_c,
+                            b200zk_plonk_pk** out) {
+  if (!ctx || !bases || !out) return B200ZK_ERR_BAD_ARG;
+  if (nb_constraints && (!ql || !qr || !qm || !qo || !qk || !wire_a || !wire_b || !wire_c)) return B200ZK_ERR_BAD_ARG;
+  const size_t size_system = nb_constraints + nb_public;
+  unsigned log2n = 1;
+  while (((size_t)1 << log2n) < size_system) log2n++;
+  unsigned log_big = 0;
+  while (((size_t)1 << log_big) < (size_system < 6 ? 8 : 4) * size_system) log_big++;
+  if (log_big < log2n + 2) log_big = log2n + 2;
+  if (log_big > B200ZK_MAX_LOG2N) return B200ZK_ERR_UNSUPPORTED;
+  const size_t n = (size_t)1 << log2n;
+  const unsigned nb_wires = nb_public + nb_secret ? nb_public + nb_secret : 1;
+  std::vector<uint8_t> cols[5];
+  const void* src[5] = {ql, qr, qm, qo, qk};
+  for (int k = 0; k < 5; k++) {
+    cols[k].assign(n * 32, 0);
+    if (nb_constraints) memcpy(cols[k].data() + (size_t)nb_public * 32, src[k], nb_constraints * 32);
+  }
+  const Fe4 minus_one = host::neg(HFR, HFR.one);
+  for (unsigned i = 0; i < nb_public; i++) memcpy(cols[0].data() + (size_t)i * 32, minus_one.l, 32);  // -PUB_i + qk_i = 0
+  std::vector<uint32_t> lro(3 * n, 0);
+  for (unsigned i = 0; i < nb_public; i++) lro[i] = i;
+  for (size_t i = 0; i < nb_constraints; i++) {
+    if (wire_a[i] >= nb_wires || wire_b[i] >= nb_wires || wire_c[i] >= nb_wires) return B200ZK_ERR_BAD_ARG;
+    lro[nb_public + i] = wire_a[i];
+    lro[n + nb_public + i] = wire_b[i];
+    lro[2 * n + nb_public + i] = wire_c[i];
+  }
+  std::vector<int64_t> perm(3 * n, -1), cycle(nb_wires, -1);
+  for (size_t i = 0; i < 3 * n; i++) {
+    if (cycle[lro[i]] != -1) perm[i] = cycle[lro[i]];
+    cycle[lro[i]] = (int64_t)i;
+  }
+  for (size_t i = 0; i < 3 * n; i++)
+    if (perm[i] == -1) perm[i] = cycle[lro[i]];
+  return b200zk_plonk_setup(ctx, bases, log2n, log_big, nb_public, nb_wires, cols[0].data(), cols[1].data(), cols[2].data(),
+                            cols[3].data(), cols[4].data(), perm.data(), lro.data(), out);
+}
+
 void b200zk_plonk_pk_free(b200zk_ctx* ctx, b200zk_plonk_pk* pk) {
   if (!pk) return;
   if (ctx) {

@@ -175,7 +175,35 @@ class ProvingKey:
 
     @classmethod
     def Setup(cls, cs: SparseR1CS, srs: SRS, ctx: Optional[Context] = None) -> "ProvingKey":
-        """plonk.Setup(spr, srs): rows = [placeholders | constraints | padding]."""
+        """plonk.Setup(spr, srs) through b200zk_plonk_setup_r1cs: the row layout [placeholders | constraints | padding]
+        and gnark's permutation are built inside the library (C++); this wrapper only marshals the columns."""
+        self = cls()
+        self.ctx = ctx or srs.ctx
+        self.srs = srs
+        size_system = cs.nb_constraints + cs.nb_public
+        self.log2n = max(_next_pow2_log(size_system), 1)
+        self.n = 1 << self.log2n
+        self.log2n_big = max(_next_pow2_log((8 if size_system < 6 else 4) * size_system), self.log2n + 2)
+        self.nb_public = cs.nb_public
+        self.nb_wires = max(cs.nb_public + cs.nb_secret, 1)
+        cols = [np.ascontiguousarray(fr_to_mont(v)) if len(v) else np.zeros(32, dtype=np.uint8)
+                for v in (cs.ql, cs.qr, cs.qm, cs.qo, cs.qk)]
+        wires = [np.ascontiguousarray(np.asarray(v, dtype=np.uint32)) if len(v) else np.zeros(1, dtype=np.uint32)
+                 for v in (cs.a, cs.b, cs.c)]
+        lib, h = self.ctx.lib, self.ctx.handle
+        out = C.c_void_p()
+        rc = lib.b200zk_plonk_setup_r1cs(h, srs.handle, cs.nb_public, cs.nb_secret, cs.nb_constraints,
+                                         *[c.ctypes.data for c in cols], *[w.ctypes.data for w in wires], C.byref(out))
+        _lib.check(h, rc)
+        self.handle = out
+        vk = np.zeros(8 * 64, dtype=np.uint8)
+        _lib.check(h, lib.b200zk_plonk_vk(h, self.handle, vk.ctypes.data))
+        self.vk_points = [vk[64 * i: 64 * i + 64].tobytes() for i in range(8)]
+        return self
+
+    @classmethod
+    def SetupPy(cls, cs: SparseR1CS, srs: SRS, ctx: Optional[Context] = None) -> "ProvingKey":
+        """Same as Setup with the row layout / permutation built in numpy (cross-check of the C++ builder)."""
         self = cls()
         self.ctx = ctx or srs.ctx
         self.srs = srs

@@ -32,9 +32,12 @@ def check_against_oracle(ctx, cs_o: pl.SparseR1CS, witness, srs_size: int, seed:
     if precompute:
         srs_d.precompute()
     pk_o = pl.setup(cs_o, srs_o)
-    pk_d = zkp.ProvingKey.Setup(to_product_cs(cs_o), srs_d, ctx)
+    pk_py = zkp.ProvingKey.SetupPy(to_product_cs(cs_o), srs_d, ctx)      # numpy row builder
+    assert pk_py.permutation.tolist() == pk_o.permutation
+    pk_d = zkp.ProvingKey.Setup(to_product_cs(cs_o), srs_d, ctx)         # C++ row builder (b200zk_plonk_setup_r1cs)
     assert (pk_d.log2n, pk_d.log2n_big) == (pk_o.n.bit_length() - 1, pk_o.n_big.bit_length() - 1)
-    assert pk_d.permutation.tolist() == pk_o.permutation
+    assert pk_py.vk_points == pk_d.vk_points
+    pk_py.close()
     vk = pk_o.vk
     want_vk = [o.g1_to_bytes([p]) for p in vk.S + [vk.Ql, vk.Qr, vk.Qm, vk.Qo, vk.Qk]]
     assert pk_d.vk_points == want_vk
