@@ -105,6 +105,12 @@ int b200zk_bases_wrap_dev(b200zk_ctx* ctx, const void* g1_affine_dev, size_t n, 
  * (/root/reference/gnark_backend_ffi/backend/common.go:137, main.go:176).  alpha: one Montgomery-form fr.Element;
  * first > 0 produces the point-range shard of one GPU. */
 int b200zk_srs_generate(b200zk_ctx* ctx, const void* alpha_host, size_t first, size_t n, b200zk_bases** out);
+/* Bases from / to gnark's COMPRESSED G1 encoding (G1Affine.Bytes(): 32-byte big-endian X, flag bits 10 / 11 / 01 in the
+ * top byte), the element format of kzg.SRS.WriteTo / ReadFrom — i.e. of the srs.hex cache the reference re-reads on
+ * every FFI call (/root/reference/gnark_backend_ffi/backend/common.go:86-105, :107-125).  Decompression (one fp square
+ * root per point) and compression run on the device; a malformed / off-curve point fails with B200ZK_ERR_BAD_ARG. */
+int b200zk_bases_upload_compressed(b200zk_ctx* ctx, const void* compressed_host, size_t n, b200zk_bases** out);
+int b200zk_bases_download_compressed(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first, size_t n, void* out_host);
 /* copy bases[first .. first+n) back to the host (64 B each), e.g. to serialise a generated SRS */
 int b200zk_bases_download(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first, size_t n, void* out_host);
 /* One-time precomputation for static bases (the SRS does not change between commitments): stores the window

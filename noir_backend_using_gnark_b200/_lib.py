@@ -72,6 +72,8 @@ def load() -> C.CDLL:
         "b200zk_bases_wrap_dev": (i, [vp, vp, sz, C.POINTER(vp)]),
         "b200zk_srs_generate": (i, [vp, vp, sz, sz, C.POINTER(vp)]),
         "b200zk_bases_download": (i, [vp, vp, sz, sz, vp]),
+        "b200zk_bases_upload_compressed": (i, [vp, vp, sz, C.POINTER(vp)]),
+        "b200zk_bases_download_compressed": (i, [vp, vp, sz, sz, vp]),
         "b200zk_bases_precompute": (i, [vp, vp, i]),
         "b200zk_bases_free": (None, [vp, vp]),
         "b200zk_bases_len": (sz, [vp]),

@@ -199,6 +199,27 @@ class SRS:
         self.n = int(size)
         return self
 
+    @classmethod
+    def FromCompressed(cls, compressed: bytes, ctx: Optional[Context] = None) -> "SRS":
+        """kzg.SRS.ReadFrom's G1 part: n x 32-byte compressed points (G1Affine.Bytes()), decompressed on the device."""
+        self = cls.__new__(cls)
+        self.ctx = ctx or default_context()
+        ptr, keep = _host_ptr(compressed)
+        n = (keep.nbytes if hasattr(keep, "nbytes") else len(compressed)) // 32
+        out = C.c_void_p()
+        _lib.check(self.ctx.handle, self.ctx.lib.b200zk_bases_upload_compressed(self.ctx.handle, ptr, n, C.byref(out)))
+        self.handle = out
+        self.n = n
+        return self
+
+    def download_compressed(self, first: int = 0, n: Optional[int] = None) -> bytes:
+        """kzg.SRS.WriteTo's G1 part (without the u32 length prefix): compressed on the device."""
+        n = self.n - first if n is None else n
+        out = np.zeros(max(n, 1) * 32, dtype=np.uint8)
+        rc = self.ctx.lib.b200zk_bases_download_compressed(self.ctx.handle, self.handle, first, n, out.ctypes.data)
+        _lib.check(self.ctx.handle, rc)
+        return out[: n * 32].tobytes()
+
     def precompute(self, c: int = 0) -> "SRS":
         """One-time window-multiple table for these (static) bases: faster MSMs, W times the memory."""
         _lib.check(self.ctx.handle, self.ctx.lib.b200zk_bases_precompute(self.ctx.handle, self.handle, int(c)))

@@ -322,6 +322,40 @@ int b200zk_srs_generate(b200zk_ctx* ctx, const void* alpha_host, size_t first, s
   return B200ZK_OK;
 }
 
+int b200zk_bases_upload_compressed(b200zk_ctx* ctx, const void* compressed_host, size_t n, b200zk_bases** out) {
+  B200ZK_TRY(enter(ctx));
+  if (!out || (n && !compressed_host)) return B200ZK_ERR_BAD_ARG;
+  *out = nullptr;
+  b200zk_bases* b = new (std::nothrow) b200zk_bases();
+  if (!b) return B200ZK_ERR_OOM;
+  void* dev = nullptr;
+  cudaError_t e = cudaMalloc(&dev, (n ? n : 1) * 64);
+  if (e != cudaSuccess) {
+    delete b;
+    return set_cuda_error(ctx, e, "cudaMalloc(bases)");
+  }
+  unsigned bad = 0;
+  int rc = n ? srs_decompress_run(ctx, compressed_host, n, dev, &bad) : B200ZK_OK;
+  if (rc == B200ZK_OK && bad != 0) rc = B200ZK_ERR_BAD_ARG;  // a point is not on the curve / malformed encoding
+  if (rc != B200ZK_OK) {
+    cudaFree(dev);
+    delete b;
+    return rc;
+  }
+  b->dev = dev;
+  b->n = n;
+  b->owned = true;
+  *out = b;
+  return B200ZK_OK;
+}
+
+int b200zk_bases_download_compressed(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first, size_t n, void* out_host) {
+  B200ZK_TRY(enter(ctx));
+  if (!bases || !out_host || first > bases->n || n > bases->n - first) return B200ZK_ERR_BAD_ARG;
+  if (n == 0) return B200ZK_OK;
+  return srs_compress_run(ctx, (const char*)bases->dev + first * 64, n, out_host);
+}
+
 int b200zk_bases_download(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first, size_t n, void* out_host) {
   B200ZK_TRY(enter(ctx));
   if (!bases || !out_host || first > bases->n || n > bases->n - first) return B200ZK_ERR_BAD_ARG;

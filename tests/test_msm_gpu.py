@@ -235,3 +235,32 @@ def test_full_size_2_24_table_vs_classic_vs_shards(ctx):
     assert classic == table == res.cpu().numpy().tobytes()
     assert classic != b"\0" * 64
     srs.close()
+
+
+def test_srs_compressed_roundtrip_matches_gnark_encoding(ctx):
+    """kzg.SRS file format (compressed G1): device compression == the oracle's G1Affine.Bytes(), device decompression
+    (fp square root + sign flag) gives the points back; off-curve input is rejected."""
+    from oracle import plonk as pl
+
+    alpha = o.random_fr(1, 0xB2000005)[0]
+    n = 300
+    srs = zk.SRS.NewSRS(n, o.fr_to_mont_bytes([alpha]), ctx)
+    pts = o.g1_from_bytes(srs.download())
+    comp = srs.download_compressed()
+    assert comp == b"".join(pl.g1_compress(p) for p in pts)
+    comp = bytearray(comp)
+    comp[5 * 32: 6 * 32] = pl.g1_compress(None)                 # an infinity entry
+    back = zk.SRS.FromCompressed(bytes(comp), ctx)
+    want = list(pts)
+    want[5] = None
+    assert o.g1_from_bytes(back.download()) == want
+    # x = 4 is not on the curve (4^3 + 3 = 67 is a non-residue mod p? checked below) -> rejected
+    x = 4
+    while pow((x ** 3 + 3) % o.P_MOD, (o.P_MOD - 1) // 2, o.P_MOD) == 1:
+        x += 1
+    badpt = bytearray(x.to_bytes(32, "big"))
+    badpt[0] |= 0x80
+    with pytest.raises(zk.B200zkError):
+        zk.SRS.FromCompressed(bytes(badpt), ctx)
+    srs.close()
+    back.close()
