@@ -44,9 +44,10 @@ struct b200zk_bases {
   const void* dev = nullptr;  // n x 64 B affine points
   size_t n = 0;
   bool owned = false;
-  // optional window table (b200zk_bases_precompute): table[j*n + i] = 2^(tab_c*j) * P_i, j < tab_W; row 0 = the bases
+  // optional window table (b200zk_bases_precompute): table[j*n + i] = 2^tab_wstart[j] * P_i, j < tab_W; row 0 = the bases
   void* table = nullptr;
   unsigned tab_c = 0, tab_W = 0;
+  uint8_t tab_wstart[65] = {0};  // window j covers scalar bits [tab_wstart[j], tab_wstart[j+1])
 };
 
 struct b200zk_ctx {

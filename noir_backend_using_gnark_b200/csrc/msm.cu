@@ -34,7 +34,7 @@ static constexpr int SLICE = 1024;             // chunk results per CTA in the b
 static constexpr int MAX_PLANES = 24;
 
 struct MsmShape {
-  unsigned c;           // window bits
+  unsigned c;           // window bits (the widest window in table mode)
   unsigned W;           // number of windows
   unsigned B;           // buckets per bucket set = 2^(c-1)
   unsigned nsets;       // bucket sets: W (classic) or 1 (precomputed)
@@ -42,26 +42,40 @@ struct MsmShape {
   unsigned tab_stride;  // table index = w * tab_stride + point index   (0 or table row length)
   unsigned first;       // index of the first base used
   unsigned big_len;     // runs longer than this go to the cooperative path
+  // window w covers scalar bits [wstart[w], wstart[w+1]); classic mode: uniform c-bit windows.  Table mode splits the
+  // 255 bits (254 scalar bits + one spare bit that absorbs the last carry) EVENLY over W windows, so the top window
+  // is as wide as the others instead of holding only 254 - c*(W-1) bits (which funnels n entries into a few buckets)
+  uint8_t wstart[MAX_WINDOWS + 1];
 };
+
+static void uniform_windows(MsmShape& sh) {
+  for (unsigned w = 0; w <= sh.W && w <= MAX_WINDOWS; w++) {
+    unsigned b = w * sh.c;
+    sh.wstart[w] = (uint8_t)(b > 255 ? 255 : b);
+  }
+}
 
 // signed-digit recoding of one scalar; calls f(w, digit) for every window (digit in [-B, B-1])
 template <class F>
 __device__ __forceinline__ void for_each_digit(const Fr& s, const MsmShape& sh, F f) {
   unsigned carry = 0;
-  const unsigned mask = (1u << sh.c) - 1u;
   for (unsigned w = 0; w < sh.W; w++) {
-    const unsigned bit = w * sh.c;
+    const unsigned bit = sh.wstart[w];
+    const unsigned width = (unsigned)sh.wstart[w + 1] - bit;   // 0 only for classic windows entirely above bit 255
     const unsigned limb = bit >> 5, off = bit & 31;
     unsigned v = 0;
-    if (limb < 8) {
+    if (width) {
       unsigned lo = s.l[limb];
       unsigned hi = limb + 1 < 8 ? s.l[limb + 1] : 0u;
-      v = (unsigned)((((uint64_t)hi << 32) | lo) >> off) & mask;
+      v = (unsigned)((((uint64_t)hi << 32) | lo) >> off) & ((1u << width) - 1u);
     }
+    // signed digit in [-2^(cw-1), 2^(cw-1)) for a cw-bit window (classic windows clipped at bit 255 keep cw = c)
+    const unsigned cw = width && sh.tab_stride ? width : sh.c;
+    const int half = 1 << (cw - 1);
     int d = (int)(v + carry);
     carry = 0;
-    if (d >= (int)sh.B) {  // d in [B, 2B] -> d - 2^c in [-B, 0]
-      d -= (int)(2 * sh.B);
+    if (d >= half) {
+      d -= 2 * half;
       carry = 1;
     }
     f(w, d);
@@ -400,8 +414,9 @@ __global__ void copy_u32_kernel(const unsigned* __restrict__ src, unsigned* __re
 // the per-window numerators and prefix products are parked in `tmp`).
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) msm_precompute_kernel(const void* __restrict__ table, size_t n, size_t first,
-                                                             size_t count, unsigned c, unsigned W, void* __restrict__ tmp,
+                                                             size_t count, MsmShape sh, void* __restrict__ tmp,
                                                              void* __restrict__ table_out) {
+  const unsigned W = sh.W;
   size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (t >= count) return;
   const size_t i = first + t;
@@ -417,7 +432,8 @@ __global__ void __launch_bounds__(128) msm_precompute_kernel(const void* __restr
   acc.zzz = fe_one<FpParams>();
   Fp pre = fe_one<FpParams>();
   for (unsigned j = 1; j < W; j++) {
-    for (unsigned k = 0; k < c; k++) g1_double(acc);
+    const unsigned steps = (unsigned)sh.wstart[j] - (unsigned)sh.wstart[j - 1];   // row j = 2^wstart[j] * P
+    for (unsigned k = 0; k < steps; k++) g1_double(acc);
     Fp zz3 = fe_mul(acc.zz, acc.zzz);
     G1XYZZ q;
     q.x = fe_mul(acc.x, acc.zzz);  // x = X/ZZ  = X*ZZZ / (ZZ*ZZZ)
@@ -462,16 +478,30 @@ int msm_precompute_run(b200zk_ctx* ctx, b200zk_bases* bases, int c_req) {
   if (n < 1024) return B200ZK_OK;  // not worth it: the classic path is used
   unsigned lg = 0;
   while (((size_t)1 << (lg + 1)) <= n) lg++;
-  unsigned c;
-  if (c_req) c = (unsigned)c_req;
-  else if (lg >= 23) c = 22;   // W = 12, top window 12 bits
-  else if (lg >= 20) c = 20;   // W = 13, top window 14 bits
-  else if (lg >= 17) c = 17;   // W = 15, top window 16 bits
-  else if (lg >= 14) c = 15;   // W = 17, top window 14 bits
-  else c = 13;                 // W = 20, top window 7 bits
-  if (c < 10) c = 10;
-  if (c > 23) c = 23;
-  const unsigned W = (255 + c - 1) / c;
+  // number of windows from the size (or from a requested maximum width c_req): W windows of 255/W bits (+1 for the
+  // first 255 % W of them)
+  unsigned W;
+  if (c_req) W = (255 + (unsigned)c_req - 1) / (unsigned)c_req;
+  else if (lg >= 23) W = 12;   // widths 22,22,22,21 x9  -> 2^21 buckets
+  else if (lg >= 20) W = 13;   // widths 20 x8, 19 x5     -> 2^19 buckets
+  else if (lg >= 17) W = 15;   // widths 17 x15           -> 2^16 buckets
+  else if (lg >= 14) W = 17;   // widths 15 x17           -> 2^14 buckets
+  else W = 20;                 // widths 13 x15, 12 x5    -> 2^12 buckets
+  if (W > MAX_WINDOWS) W = MAX_WINDOWS;
+  MsmShape tsh;
+  memset(&tsh, 0, sizeof(tsh));
+  tsh.W = W;
+  {
+    const unsigned base = 255 / W, rem = 255 % W;
+    unsigned pos = 0;
+    for (unsigned w = 0; w < W; w++) {
+      tsh.wstart[w] = (uint8_t)pos;
+      pos += base + (w < rem ? 1 : 0);
+    }
+    tsh.wstart[W] = 255;
+    tsh.c = base + (rem ? 1 : 0);
+  }
+  const unsigned c = tsh.c;
   if ((size_t)W * n >= ((size_t)1 << 31)) return B200ZK_ERR_UNSUPPORTED;
   void* table = nullptr;
   cudaError_t e = cudaMalloc(&table, (size_t)W * n * 64);
@@ -486,7 +516,7 @@ int msm_precompute_run(b200zk_ctx* ctx, b200zk_bases* bases, int c_req) {
   e = cudaMemcpyAsync(table, bases->dev, n * 64, cudaMemcpyDeviceToDevice, ctx->stream);
   for (size_t first = 0; first < n && e == cudaSuccess; first += chunk) {
     const size_t count = first + chunk <= n ? chunk : n - first;
-    msm_precompute_kernel<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(table, n, first, count, c, W, tmp, table);
+    msm_precompute_kernel<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(table, n, first, count, tsh, tmp, table);
     ctx->launches++;
     e = cudaGetLastError();
   }
@@ -499,6 +529,7 @@ int msm_precompute_run(b200zk_ctx* ctx, b200zk_bases* bases, int c_req) {
   bases->table = table;
   bases->tab_c = c;
   bases->tab_W = W;
+  memcpy(bases->tab_wstart, tsh.wstart, sizeof(tsh.wstart));
   return B200ZK_OK;
 }
 
@@ -514,6 +545,7 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
     return B200ZK_OK;
   }
   MsmShape sh;
+  memset(&sh, 0, sizeof(sh));
   const bool use_table = bases->table && !ctx->forced_window && n * 16 >= bases->n;
   const void* base_ptr;
   if (use_table) {
@@ -523,6 +555,7 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
     sh.nsets = 1;
     sh.key_stride = 0;
     sh.tab_stride = (unsigned)bases->n;
+    memcpy(sh.wstart, bases->tab_wstart, sizeof(sh.wstart));
     base_ptr = bases->table;
   } else {
     sh.c = ctx->forced_window ? (unsigned)ctx->forced_window : choose_window(n);
@@ -533,6 +566,7 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
     sh.nsets = sh.W;
     sh.key_stride = sh.B;
     sh.tab_stride = 0;
+    uniform_windows(sh);
     base_ptr = bases->dev;
   }
   sh.first = (unsigned)first_base;
