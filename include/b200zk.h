@@ -130,6 +130,9 @@ int b200zk_msm_g1_dev(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_b
                       size_t n, void* out_dev, int out_kind);
 /* out_affine_dev (64 B) = canonical affine of the sum of `count` extended-Jacobian partials (128 B each). */
 int b200zk_g1_sum_dev(b200zk_ctx* ctx, const void* partials_dev, size_t count, void* out_affine_dev);
+/* tests / tuning: 0 / 1 = one-level scatter (default: all of a point's returning atomics in flight at once),
+ * 2 = two-level scatter (partition by high bucket bits, then shared-memory cursors; slower on B200, kept for comparison) */
+int b200zk_msm_set_flat_scatter(b200zk_ctx* ctx, int on);
 /* force the Pippenger window size (0 = choose from n); for tests and tuning */
 int b200zk_msm_set_window(b200zk_ctx* ctx, int c);
 

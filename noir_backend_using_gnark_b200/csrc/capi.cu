@@ -78,6 +78,7 @@ void b200zk_destroy(b200zk_ctx* ctx) {
   free_buf(ctx->msm_small);
   free_buf(ctx->msm_scan_tmp);
   free_buf(ctx->msm_big);
+  free_buf(ctx->msm_part);
   cudaStreamDestroy(ctx->stream);
   if (ctx->side) cudaStreamDestroy(ctx->side);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -402,6 +403,12 @@ int b200zk_microbench(b200zk_ctx* ctx, int which, double* out_ops_per_s) {
 int b200zk_ntt_set_radix2(b200zk_ctx* ctx, int on) {
   if (!ctx) return B200ZK_ERR_BAD_ARG;
   ctx->ntt_radix2 = on != 0;
+  return B200ZK_OK;
+}
+
+int b200zk_msm_set_flat_scatter(b200zk_ctx* ctx, int on) {
+  if (!ctx) return B200ZK_ERR_BAD_ARG;
+  ctx->msm_flat_scatter = on;  // 0/1: one-level scatter (default), 2: two-level (partition + shared-memory cursors)
   return B200ZK_OK;
 }
 

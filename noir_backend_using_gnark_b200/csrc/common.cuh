@@ -59,6 +59,7 @@ struct b200zk_ctx {
   uint64_t launches = 0;
   char cuda_err[256] = {0};
   int forced_window = 0;
+  int msm_flat_scatter = 0;  // tests: force the one-level (global-atomic) scatter
   int ntt_radix2 = 0;  // tests: force the radix-2 pass kernel
   bool profiling = false;
   std::vector<b200zk::PhaseRecord> records;
@@ -67,7 +68,7 @@ struct b200zk_ctx {
   b200zk::DeviceBuf stage;
   // MSM workspace (grown on demand, reused across calls)
   b200zk::DeviceBuf msm_digits, msm_sorted, msm_counts, msm_starts, msm_cursor, msm_buckets, msm_tmp, msm_small,
-      msm_scan_tmp, msm_big;
+      msm_scan_tmp, msm_big, msm_part;
 };
 
 namespace b200zk {

@@ -111,6 +111,10 @@ __global__ void __launch_bounds__(256) msm_hist_kernel(const uint4* __restrict__
   });
 }
 
+// Every thread first issues ALL of its point's returning atomics (one per window, positions kept in registers) and
+// only then the dependent stores: W atomics in flight per thread instead of one (the kernel is bound by the latency
+// of the returning atomic, not by its throughput: ncu long_scoreboard 200 cycles per issue at 88 % occupancy).
+template <int MAXW>
 __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint4* __restrict__ scalars, size_t n, MsmShape sh,
                                                           unsigned* __restrict__ cursor, unsigned* __restrict__ sorted) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -118,23 +122,122 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint4* __restric
   if (i >= n) return;
   const unsigned lane = threadIdx.x & 31;
   Fr s = load_scalar_regular(scalars, i);
-  for_each_digit(s, sh, [&](unsigned w, int d) {
-    const unsigned mag = d < 0 ? (unsigned)(-d) : (unsigned)d;
-    const unsigned key = w * sh.key_stride + (mag - 1);
-    const unsigned entry = (w * sh.tab_stride + sh.first + (unsigned)i) | (d < 0 ? 0x80000000u : 0u);
-    if (w + 1 == sh.W) {
-      // warp-aggregated cursor bump for the narrow top window (see msm_hist_kernel)
-      const unsigned grp = __match_any_sync(active, d != 0 ? key : 0xffffffffu);
-      const unsigned leader = (unsigned)(__ffs(grp) - 1);
-      unsigned base = 0;
-      if (d != 0 && lane == leader) base = atomicAdd(&cursor[key], (unsigned)__popc(grp));
-      base = __shfl_sync(grp, base, leader);
-      if (d != 0) sorted[base + __popc(grp & ((1u << lane) - 1u))] = entry;
-    } else if (d != 0) {
-      unsigned pos = atomicAdd(&cursor[key], 1u);
-      sorted[pos] = entry;
+  unsigned pos[MAXW], entry[MAXW];
+  unsigned carry = 0;
+#pragma unroll
+  for (int w = 0; w < MAXW; w++) {
+    pos[w] = 0xffffffffu;
+    entry[w] = 0;
+    if ((unsigned)w < sh.W) {
+      const unsigned bit = sh.wstart[w];
+      const unsigned width = (unsigned)sh.wstart[w + 1] - bit;
+      const unsigned limb = bit >> 5, off = bit & 31;
+      unsigned v = 0;
+      if (width) {
+        unsigned lo = s.l[limb];
+        unsigned hi = limb + 1 < 8 ? s.l[limb + 1] : 0u;
+        v = (unsigned)((((uint64_t)hi << 32) | lo) >> off) & ((1u << width) - 1u);
+      }
+      const unsigned cw = width && sh.tab_stride ? width : sh.c;
+      const int half = 1 << (cw - 1);
+      int d = (int)(v + carry);
+      carry = 0;
+      if (d >= half) {
+        d -= 2 * half;
+        carry = 1;
+      }
+      const unsigned mag = d < 0 ? (unsigned)(-d) : (unsigned)d;
+      const unsigned key = (unsigned)w * sh.key_stride + (mag - 1);
+      entry[w] = ((unsigned)w * sh.tab_stride + sh.first + (unsigned)i) | (d < 0 ? 0x80000000u : 0u);
+      if ((unsigned)w + 1 == sh.W) {
+        // warp-aggregated cursor bump for the last window (classic mode: narrow top window, see msm_hist_kernel)
+        const unsigned grp = __match_any_sync(active, d != 0 ? key : 0xffffffffu);
+        const unsigned leader = (unsigned)(__ffs(grp) - 1);
+        unsigned base = 0;
+        if (d != 0 && lane == leader) base = atomicAdd(&cursor[key], (unsigned)__popc(grp));
+        base = __shfl_sync(grp, base, leader);
+        if (d != 0) pos[w] = base + __popc(grp & ((1u << lane) - 1u));
+      } else if (d != 0) {
+        pos[w] = atomicAdd(&cursor[key], 1u);
+      }
     }
-  });
+  }
+#pragma unroll
+  for (int w = 0; w < MAXW; w++)
+    if (pos[w] != 0xffffffffu) sorted[pos[w]] = entry[w];
+}
+
+// ---- 3'. two-level scatter: partition by the high bits of the bucket id, then counting-sort each partition in
+// shared memory.  The one-level scatter above needs one RETURNING global atomic per entry (~31 G/s on B200, 6x slower
+// than non-returning reductions) and writes 4 bytes at random over hundreds of MB (8.7x DRAM write amplification, ncu).
+// Here the only returning global atomics are one per (CTA tile, partition); entries travel in ~1.5 KB runs to their
+// partition, and the final 4-byte stores of a partition land in a few MB that stay in L2.
+static constexpr int PART_TILE_PTS = 2048;    // points per CTA in the partition pass (8 per thread)
+static constexpr int MAX_PARTS = 1024;
+
+__global__ void __launch_bounds__(256) msm_partition_kernel(const uint4* __restrict__ scalars, size_t n, MsmShape sh,
+                                                            unsigned part_log, unsigned nparts,
+                                                            unsigned* __restrict__ part_cursor, uint2* __restrict__ tmp) {
+  __shared__ unsigned cnt[MAX_PARTS];
+  __shared__ unsigned base[MAX_PARTS];
+  for (unsigned p = threadIdx.x; p < nparts; p += blockDim.x) cnt[p] = 0;
+  __syncthreads();
+  const size_t tile0 = (size_t)blockIdx.x * PART_TILE_PTS;
+  // pass 1: count this tile's entries per partition
+  for (unsigned k = 0; k < PART_TILE_PTS / 256; k++) {
+    const size_t i = tile0 + k * 256 + threadIdx.x;
+    if (i < n) {
+      Fr s = load_scalar_regular(scalars, i);
+      for_each_digit(s, sh, [&](unsigned w, int d) {
+        if (d != 0) {
+          const unsigned mag = d < 0 ? (unsigned)(-d) : (unsigned)d;
+          atomicAdd(&cnt[(w * sh.key_stride + (mag - 1)) >> part_log], 1u);
+        }
+      });
+    }
+  }
+  __syncthreads();
+  // reserve one run per partition in the partition-ordered scratch array
+  for (unsigned p = threadIdx.x; p < nparts; p += blockDim.x) {
+    const unsigned c = cnt[p];
+    base[p] = c ? atomicAdd(&part_cursor[p], c) : 0u;
+    cnt[p] = 0;
+  }
+  __syncthreads();
+  // pass 2: emit (bucket, entry) records into the reserved runs
+  for (unsigned k = 0; k < PART_TILE_PTS / 256; k++) {
+    const size_t i = tile0 + k * 256 + threadIdx.x;
+    if (i < n) {
+      Fr s = load_scalar_regular(scalars, i);
+      for_each_digit(s, sh, [&](unsigned w, int d) {
+        if (d != 0) {
+          const unsigned mag = d < 0 ? (unsigned)(-d) : (unsigned)d;
+          const unsigned key = w * sh.key_stride + (mag - 1);
+          const unsigned p = key >> part_log;
+          const unsigned slot = atomicAdd(&cnt[p], 1u);
+          tmp[base[p] + slot] = make_uint2(key, (w * sh.tab_stride + sh.first + (unsigned)i) | (d < 0 ? 0x80000000u : 0u));
+        }
+      });
+    }
+  }
+}
+
+// one CTA per partition: per-bucket cursors live in shared memory
+__global__ void __launch_bounds__(1024) msm_scatter_local_kernel(const uint2* __restrict__ tmp, const unsigned* __restrict__ starts,
+                                                                 unsigned part_log, unsigned nbuckets,
+                                                                 unsigned* __restrict__ sorted) {
+  extern __shared__ unsigned cur[];
+  const unsigned psize = 1u << part_log;
+  const unsigned b0 = blockIdx.x << part_log;
+  const unsigned b1 = b0 + psize < nbuckets ? b0 + psize : nbuckets;
+  for (unsigned b = threadIdx.x; b < b1 - b0; b += blockDim.x) cur[b] = starts[b0 + b];
+  __syncthreads();
+  const unsigned lo = starts[b0], hi = starts[b1];
+  for (unsigned j = lo + threadIdx.x; j < hi; j += blockDim.x) {
+    const uint2 rec = tmp[j];
+    const unsigned pos = atomicAdd(&cur[rec.x - b0], 1u);
+    sorted[pos] = rec.y;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -403,6 +506,11 @@ __global__ void iota_u32_kernel(unsigned* __restrict__ dst, size_t n) {
   if (i < n) dst[i] = (unsigned)i;
 }
 
+__global__ void copy_strided_u32_kernel(const unsigned* __restrict__ src, unsigned* __restrict__ dst, unsigned n, unsigned shift) {
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[(size_t)i << shift];
+}
+
 __global__ void copy_u32_kernel(const unsigned* __restrict__ src, unsigned* __restrict__ dst, size_t n) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i < n) dst[i] = src[i];
@@ -645,10 +753,39 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
                                                                (const unsigned*)iota, order, (int)nbuckets, 0, 32, st));
     ctx->launches += 4;
   }
-  {
+  if (total >= ((size_t)1 << 18) && ctx->msm_flat_scatter == 2) {
+    // two-level scatter (large problems): partition, then shared-memory counting sort per partition
+    PhaseTimer pt(ctx, PH_MSM_SCATTER);
+    unsigned lgb = 0;
+    while ((1u << lgb) < nbuckets) lgb++;
+    unsigned part_log = lgb > 7 ? lgb - 7 : 0;
+    if (part_log > 14) part_log = 14;
+    if (part_log < 8) part_log = 8;
+    while (((nbuckets + (1u << part_log) - 1) >> part_log) > (unsigned)MAX_PARTS) part_log++;
+    const unsigned nparts = (nbuckets + (1u << part_log) - 1) >> part_log;
+    B200ZK_TRY(ensure(ctx, ctx->msm_part, total * sizeof(uint2) + (size_t)MAX_PARTS * 4));
+    uint2* tmp2 = (uint2*)ctx->msm_part.p;
+    unsigned* part_cursor = (unsigned*)((char*)ctx->msm_part.p + total * sizeof(uint2));
+    // partition p owns sorted[starts[p << part_log] ...): its cursor starts there
+    copy_strided_u32_kernel<<<(nparts + 255) / 256, 256, 0, st>>>(starts, part_cursor, nparts, part_log);
+    B200ZK_LAUNCH_CHECK(ctx, "copy_strided_u32_kernel");
+    const unsigned tiles = (unsigned)((n + PART_TILE_PTS - 1) / PART_TILE_PTS);
+    msm_partition_kernel<<<tiles, 256, 0, st>>>((const uint4*)scalars_dev, n, sh, part_log, nparts, part_cursor, tmp2);
+    B200ZK_LAUNCH_CHECK(ctx, "msm_partition_kernel");
+    const size_t shm = (size_t)4 << part_log;
+    if (shm > 48 * 1024)
+      B200ZK_CUDA(ctx, cudaFuncSetAttribute(msm_scatter_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+    msm_scatter_local_kernel<<<nparts, 1024, shm, st>>>(tmp2, starts, part_log, nbuckets, sorted);
+    B200ZK_LAUNCH_CHECK(ctx, "msm_scatter_local_kernel");
+  } else {
     PhaseTimer pt(ctx, PH_MSM_SCATTER);
     unsigned blocks = (unsigned)((n + 255) / 256);
-    msm_scatter_kernel<<<blocks, 256, 0, st>>>((const uint4*)scalars_dev, n, sh, cursor, sorted);
+    if (sh.W <= 13)
+      msm_scatter_kernel<13><<<blocks, 256, 0, st>>>((const uint4*)scalars_dev, n, sh, cursor, sorted);
+    else if (sh.W <= 20)
+      msm_scatter_kernel<20><<<blocks, 256, 0, st>>>((const uint4*)scalars_dev, n, sh, cursor, sorted);
+    else
+      msm_scatter_kernel<MAX_WINDOWS><<<blocks, 256, 0, st>>>((const uint4*)scalars_dev, n, sh, cursor, sorted);
     B200ZK_LAUNCH_CHECK(ctx, "msm_scatter_kernel");
   }
   {

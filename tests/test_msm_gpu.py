@@ -264,3 +264,21 @@ def test_srs_compressed_roundtrip_matches_gnark_encoding(ctx):
         zk.SRS.FromCompressed(bytes(badpt), ctx)
     srs.close()
     back.close()
+
+
+def test_flat_and_two_level_scatter_agree(ctx):
+    """both counting-sort variants (global returning atomics / partition + shared-memory cursors), classic and table"""
+    lib = zk.load()
+    n = 1 << 17
+    pts = structured(n)
+    sc = cref.random_fr(n, 0xB2000001 + 99)
+    want = cref.msm(pts, sc, n, nthreads=cref.ncores())
+    srs = zk.SRS(pts, ctx)
+    for table in (False, True):
+        if table:
+            srs.precompute()
+        for flat in (2, 0):
+            lib.b200zk_msm_set_flat_scatter(ctx.handle, flat)
+            assert zk.MultiExp(srs, sc) == want, (table, flat)
+    lib.b200zk_msm_set_flat_scatter(ctx.handle, 0)
+    srs.close()
