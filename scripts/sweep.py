@@ -102,9 +102,37 @@ def ntt_sweep(ctx, lo, hi):
         del x
 
 
+def skew_sweep(ctx, lg):
+    """adversarial scalar sets of SURVEY.md 8d at one size: all-equal, witness-like (50 % zero, 25 % < 2^16, 25 % uniform)"""
+    n = 1 << lg
+    alpha = 0x1234567890ABCDEF1234567890ABCDEF % R
+    srs = zk.SRS.NewSRS(n, zkp.fr_to_mont([alpha]), ctx).precompute()
+    uni = images(n, 0xB2000001)
+    one = uni[:32]
+    sets = {"uniform": uni, "all_equal": np.tile(one, n)}
+    w = uni.copy().reshape(n, 32)
+    w[: n // 2] = 0
+    small = np.zeros((n // 4, 32), dtype=np.uint8)
+    small[:, :2] = uni.reshape(n, 32)[: n // 4, :2]
+    # small values must be stored in Montgomery form to be small scalars: convert through the library-free path
+    vals = [int.from_bytes(bytes(r[:2]), "little") for r in small]
+    w[n // 2: n // 2 + n // 4] = zkp.fr_to_mont(vals).reshape(-1, 32)
+    sets["witness_like"] = w.reshape(-1)
+    out = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    for name, arr in sets.items():
+        sc = torch.from_numpy(np.ascontiguousarray(arr)).cuda()
+        torch.cuda.synchronize()
+        t = timeit(ctx, lambda: zk.MultiExp(srs, sc, n=n, out=out), 3)
+        print(json.dumps({"op": "msm_skew", "log2n": lg, "set": name, "table_ms": t, "mpts": n / t / 1e3}), flush=True)
+    srs.close()
+
+
 if __name__ == "__main__":
     what = sys.argv[1]
     lo = int(sys.argv[2]) if len(sys.argv) > 2 else 16
     hi = int(sys.argv[3]) if len(sys.argv) > 3 else (26 if what == "msm" else 28)
     ctx = zk.Context(0)
-    (msm_sweep if what == "msm" else ntt_sweep)(ctx, lo, hi)
+    if what == "skew":
+        skew_sweep(ctx, lo)
+    else:
+        (msm_sweep if what == "msm" else ntt_sweep)(ctx, lo, hi)
