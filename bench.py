@@ -285,15 +285,19 @@ def run_prove(ctx, log2n: int, rank: int = 0, world: int = 1, cpu_sample_log2: i
             ts.append((time.perf_counter() - t0) * 1e3)
         return pr, ts, (ctx.launch_count - l0) // 3
 
-    proof, times, launches = timed()
     sharded = None
-    if com is not None:
-        com.attach(pk)
-        proof_s, times_s, _ = timed()
-        com.stop()
-        com.detach(pk)
-        sharded = {"gpus": world, "ms": min(times_s), "ms_all": times_s, "same_proof_bytes": proof_s.blob == proof.blob,
-                   "error": repr(com.error) if com.error else None}
+    try:
+        proof, times, launches = timed()
+        if com is not None:
+            com.attach(pk)
+            proof_s, times_s, _ = timed()
+            com.detach(pk)
+            sharded = {"gpus": world, "ms": min(times_s), "ms_all": times_s,
+                       "same_proof_bytes": proof_s.blob == proof.blob,
+                       "error": repr(com.error) if com.error else None}
+    finally:
+        if com is not None:
+            com.stop()   # always release the worker ranks, also when rank 0 failed
     # acceptance by the independent verifier (checker only: oracle/plonk.py pairing check)
     from oracle import bn254 as o
     from oracle import plonk as pl

@@ -150,6 +150,7 @@ int ntt_dist_run(b200zk_ctx* ctx, const void* src, void* dst, unsigned log2n, un
                  unsigned log2c, int half, int inverse, int decimation, int coset, void* const* peers = nullptr);
 int bit_reverse_run(b200zk_ctx* ctx, void* a_dev, unsigned log2n);
 void ntt_free_domains(b200zk_ctx* ctx);
+int ntt_prepare(b200zk_ctx* ctx, unsigned log2n);  // builds the twiddle / coset tables of a domain if missing
 int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const void* scalars_dev, size_t n,
             void* out_dev, int out_kind);
 int msm_precompute_run(b200zk_ctx* ctx, b200zk_bases* bases, int c);

@@ -106,6 +106,11 @@ static int build_domain(b200zk_ctx* ctx, unsigned log2n) {
   return B200ZK_OK;
 }
 
+int ntt_prepare(b200zk_ctx* ctx, unsigned log2n) {
+  if (log2n > B200ZK_MAX_LOG2N) return B200ZK_ERR_BAD_ARG;
+  return build_domain(ctx, log2n);
+}
+
 void ntt_free_domains(b200zk_ctx* ctx) {
   for (auto& d : ctx->domains) {
     if (!d.ready) continue;

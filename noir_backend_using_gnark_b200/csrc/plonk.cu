@@ -772,6 +772,9 @@ int b200zk_plonk_prove(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solutio
   uint8_t pts[16 * 64];
   Fe4 sc[16];
 
+  // the kernels below read the twiddle tables of both domains directly (identity polynomial, permutation support)
+  B200ZK_TRY(ntt_prepare(ctx, log2n));
+  B200ZK_TRY(ntt_prepare(ctx, logb));
   B200ZK_CUDA(ctx, cudaMemcpyAsync(pk->sol, solution_host, (size_t)pk->nb_wires * 32, cudaMemcpyHostToDevice, st));
   B200ZK_CUDA(ctx, cudaMemcpyAsync(pk->blinding, blinding_host, 9 * 32, cudaMemcpyHostToDevice, st));
 
