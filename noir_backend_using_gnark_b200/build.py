@@ -1,4 +1,5 @@
-"""In-tree build of libb200zk.so (the sm_100a CUDA library behind include/b200zk.h).
+"""In-tree build of libb200zk.so (the sm_100a CUDA library behind include/b200zk.h) and of
+libgnark_backend_b200.so (the C++ stand-in for the reference's cgo exports, include/gnark_backend_ffi.h).
 
 nvcc cross-compiles for sm_100a without a GPU; the resulting .so is git-ignored but travels with the repo
 snapshot to the GPU box.  Usage: python -m noir_backend_using_gnark_b200.build [--force]
@@ -16,6 +17,8 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIBDIR = PKG / "lib"
 LIB = LIBDIR / "libb200zk.so"
+FFI_LIB = LIBDIR / "libgnark_backend_b200.so"
+FFI_SRC = CSRC / "ffi" / "gnark_backend_ffi.cpp"
 SOURCES = ["capi.cu", "ntt.cu", "msm.cu", "srs.cu", "microbench.cu", "plonk.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -34,7 +37,9 @@ def _nvcc() -> str:
 
 def _digest() -> str:
     h = hashlib.sha256()
-    for p in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "b200zk.h"]):
+    inc = PKG.parent / "include"
+    for p in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + list((CSRC / "ffi").glob("*"))
+                    + [inc / "b200zk.h", inc / "gnark_backend_ffi.h"]):
         h.update(p.name.encode())
         h.update(p.read_bytes())
     h.update(" ".join(NVCC_FLAGS).encode())
@@ -45,7 +50,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     LIBDIR.mkdir(exist_ok=True)
     stamp = LIBDIR / "libb200zk.stamp"
     digest = _digest()
-    if not force and LIB.exists() and stamp.exists() and stamp.read_text() == digest:
+    if not force and LIB.exists() and FFI_LIB.exists() and stamp.exists() and stamp.read_text() == digest:
         return LIB
     nvcc = _nvcc()
     objdir = LIBDIR / "obj"
@@ -69,6 +74,12 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    # host-only C++ on top of the C ABI; found next to libb200zk.so through $ORIGIN
+    cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", str(FFI_LIB), str(FFI_SRC),
+           "-L" + str(LIBDIR), "-lb200zk", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed for %s:\n%s\n%s" % (FFI_SRC.name, r.stdout, r.stderr))
     stamp.write_text(digest)
     return LIB
 

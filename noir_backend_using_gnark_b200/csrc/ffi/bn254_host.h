@@ -1,0 +1,414 @@
+// Host-side BN254 for the FFI stand-in: what stays on the CPU in the reference too (gnark's plonk.Verify = two
+// pairings + a 7-term MSM, SRS G2 elements, key / proof (de)serialisation).  O(1) work per call; not the hot path.
+//   Fp / Fr   : csrc/host_field.h (4 x u64 Montgomery)
+//   Fp2       : Fp[u]/(u^2+1)
+//   G1 / G2   : affine + Jacobian (G1) host arithmetic, gnark compressed encodings (G1Affine.Bytes / G2Affine.Bytes)
+//   pairing   : optimal ate, Fp12 = Fp[w]/(w^12 - 18 w^6 + 82) with u = w^6 - 9, generic affine line functions
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#include "../host_field.h"
+#include "ffi_consts.h"
+
+namespace b200zk {
+namespace ffi {
+
+using host::Fe4;
+using host::HFP;
+using host::HFR;
+
+inline Fe4 fp_from_limbs(const uint64_t l[4]) { Fe4 r; memcpy(r.l, l, 32); return r; }
+inline Fe4 fp_zero() { Fe4 r = {{0, 0, 0, 0}}; return r; }
+inline bool fe_eq(const Fe4& a, const Fe4& b) { return memcmp(a.l, b.l, 32) == 0; }
+inline Fe4 fp_mul(const Fe4& a, const Fe4& b) { return host::mul(HFP, a, b); }
+inline Fe4 fp_add(const Fe4& a, const Fe4& b) { return host::add(HFP, a, b); }
+inline Fe4 fp_sub(const Fe4& a, const Fe4& b) { return host::sub(HFP, a, b); }
+inline Fe4 fp_neg(const Fe4& a) { return host::neg(HFP, a); }
+inline Fe4 fp_inv(const Fe4& a) { return host::inv(HFP, a); }
+inline Fe4 fp_small(uint64_t v) { return host::from_u64(HFP, v); }
+inline Fe4 fp_pow(const Fe4& a, const uint64_t e[4]) {
+  Fe4 acc = HFP.one, base = a;
+  for (int i = 0; i < 256; i++) {
+    if ((e[i / 64] >> (i % 64)) & 1) acc = fp_mul(acc, base);
+    base = fp_mul(base, base);
+  }
+  return acc;
+}
+// regular-form value > (p-1)/2 ?
+inline bool fp_lex_largest(const Fe4& a_mont) {
+  Fe4 r = host::from_mont(HFP, a_mont);
+  for (int i = 3; i >= 0; i--)
+    if (r.l[i] != P_MINUS1_DIV2[i]) return r.l[i] > P_MINUS1_DIV2[i];
+  return false;
+}
+inline void fp_to_be(const Fe4& a_mont, uint8_t out[32]) { host::marshal(HFP, a_mont, out); }
+// 32-byte big-endian -> Montgomery fp; *ok = value < p
+inline Fe4 fp_from_be(const uint8_t in[32], bool* ok) {
+  Fe4 v;
+  for (int i = 0; i < 4; i++) {
+    uint64_t w = 0;
+    for (int b = 0; b < 8; b++) w |= (uint64_t)in[31 - (8 * i + b)] << (8 * b);
+    v.l[i] = w;
+  }
+  if (ok) *ok = !host::geq(v.l, HFP.m);
+  return host::to_mont(HFP, v);
+}
+
+// ---------------------------------------------------------------------------------------------- G1
+struct G1 { Fe4 x, y; bool inf; };
+struct G1J { Fe4 x, y, z; };  // Jacobian, z = 0 -> infinity
+
+inline G1 g1_from_image(const uint8_t b[64]) {
+  G1 p;
+  memcpy(p.x.l, b, 32);
+  memcpy(p.y.l, b + 32, 32);
+  p.inf = host::is_zero(p.x) && host::is_zero(p.y);
+  return p;
+}
+inline void g1_to_image(const G1& p, uint8_t b[64]) {
+  if (p.inf) { memset(b, 0, 64); return; }
+  memcpy(b, p.x.l, 32);
+  memcpy(b + 32, p.y.l, 32);
+}
+inline G1J g1j_inf() { G1J r; r.x = HFP.one; r.y = HFP.one; r.z = fp_zero(); return r; }
+inline G1J g1j_double(const G1J& p) {
+  if (host::is_zero(p.z)) return p;
+  Fe4 A = fp_mul(p.x, p.x), B = fp_mul(p.y, p.y), C = fp_mul(B, B);
+  Fe4 t = fp_add(p.x, B);
+  Fe4 D = fp_sub(fp_sub(fp_mul(t, t), A), C);
+  D = fp_add(D, D);
+  Fe4 E = fp_add(fp_add(A, A), A), F = fp_mul(E, E);
+  G1J r;
+  r.x = fp_sub(F, fp_add(D, D));
+  Fe4 c8 = fp_add(C, C); c8 = fp_add(c8, c8); c8 = fp_add(c8, c8);
+  r.y = fp_sub(fp_mul(E, fp_sub(D, r.x)), c8);
+  r.z = fp_mul(fp_add(p.y, p.y), p.z);
+  return r;
+}
+inline G1J g1j_add_affine(const G1J& p, const G1& q) {
+  if (q.inf) return p;
+  if (host::is_zero(p.z)) { G1J r; r.x = q.x; r.y = q.y; r.z = HFP.one; return r; }
+  Fe4 z2 = fp_mul(p.z, p.z), u2 = fp_mul(q.x, z2), s2 = fp_mul(fp_mul(q.y, p.z), z2);
+  Fe4 h = fp_sub(u2, p.x), rr = fp_sub(s2, p.y);
+  if (host::is_zero(h)) {
+    if (host::is_zero(rr)) return g1j_double(p);
+    return g1j_inf();
+  }
+  Fe4 hh = fp_mul(h, h), hhh = fp_mul(h, hh), v = fp_mul(p.x, hh);
+  G1J r;
+  r.x = fp_sub(fp_sub(fp_mul(rr, rr), hhh), fp_add(v, v));
+  r.y = fp_sub(fp_mul(rr, fp_sub(v, r.x)), fp_mul(p.y, hhh));
+  r.z = fp_mul(p.z, h);
+  return r;
+}
+inline G1 g1j_to_affine(const G1J& p) {
+  G1 r;
+  if (host::is_zero(p.z)) { r.x = r.y = fp_zero(); r.inf = true; return r; }
+  Fe4 zi = fp_inv(p.z), zi2 = fp_mul(zi, zi);
+  r.x = fp_mul(p.x, zi2);
+  r.y = fp_mul(p.y, fp_mul(zi2, zi));
+  r.inf = false;
+  return r;
+}
+inline G1 g1_neg(const G1& p) { G1 r = p; if (!p.inf) r.y = fp_neg(p.y); return r; }
+// scalar given as Montgomery fr
+inline G1J g1_mul_j(const G1& p, const Fe4& k_mont) {
+  Fe4 k = host::from_mont(HFR, k_mont);
+  G1J acc = g1j_inf();
+  for (int b = 255; b >= 0; b--) {
+    acc = g1j_double(acc);
+    if ((k.l[b / 64] >> (b % 64)) & 1) acc = g1j_add_affine(acc, p);
+  }
+  return acc;
+}
+inline G1 g1_mul(const G1& p, const Fe4& k_mont) { return g1j_to_affine(g1_mul_j(p, k_mont)); }
+inline G1 g1_add(const G1& a, const G1& b) {
+  G1J j = g1j_inf();
+  j = g1j_add_affine(j, a);
+  j = g1j_add_affine(j, b);
+  return g1j_to_affine(j);
+}
+inline G1 g1_generator() { G1 g; g.x = HFP.one; g.y = fp_add(HFP.one, HFP.one); g.inf = false; return g; }
+
+// G1Affine.Bytes(): 32-byte BE X, flags 10 (smallest y) / 11 (largest y) / 01 (infinity)
+inline void g1_compress(const G1& p, uint8_t out[32]) {
+  if (p.inf) { memset(out, 0, 32); out[0] = 0x40; return; }
+  fp_to_be(p.x, out);
+  out[0] |= fp_lex_largest(p.y) ? 0xC0 : 0x80;
+}
+inline bool g1_decompress(const uint8_t in[32], G1* out) {
+  const unsigned flag = in[0] >> 6;
+  if (flag == 1) { out->x = out->y = fp_zero(); out->inf = true; return true; }
+  if (flag == 0) return false;
+  uint8_t b[32];
+  memcpy(b, in, 32);
+  b[0] &= 0x3f;
+  bool ok;
+  Fe4 x = fp_from_be(b, &ok);
+  if (!ok) return false;
+  Fe4 rhs = fp_add(fp_mul(fp_mul(x, x), x), fp_small(3));
+  Fe4 y = fp_pow(rhs, EXP_P_PLUS1_DIV4);
+  if (!fe_eq(fp_mul(y, y), rhs)) return false;
+  if (fp_lex_largest(y) != (flag == 3)) y = fp_neg(y);
+  out->x = x; out->y = y; out->inf = false;
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------- Fp2, G2
+struct Fp2 { Fe4 a0, a1; };
+inline Fp2 f2_zero() { Fp2 r; r.a0 = r.a1 = fp_zero(); return r; }
+inline Fp2 f2_one() { Fp2 r; r.a0 = HFP.one; r.a1 = fp_zero(); return r; }
+inline bool f2_is_zero(const Fp2& a) { return host::is_zero(a.a0) && host::is_zero(a.a1); }
+inline bool f2_eq(const Fp2& a, const Fp2& b) { return fe_eq(a.a0, b.a0) && fe_eq(a.a1, b.a1); }
+inline Fp2 f2_add(const Fp2& a, const Fp2& b) { Fp2 r; r.a0 = fp_add(a.a0, b.a0); r.a1 = fp_add(a.a1, b.a1); return r; }
+inline Fp2 f2_sub(const Fp2& a, const Fp2& b) { Fp2 r; r.a0 = fp_sub(a.a0, b.a0); r.a1 = fp_sub(a.a1, b.a1); return r; }
+inline Fp2 f2_neg(const Fp2& a) { Fp2 r; r.a0 = fp_neg(a.a0); r.a1 = fp_neg(a.a1); return r; }
+inline Fp2 f2_conj(const Fp2& a) { Fp2 r; r.a0 = a.a0; r.a1 = fp_neg(a.a1); return r; }
+inline Fp2 f2_mul(const Fp2& a, const Fp2& b) {
+  Fp2 r;
+  r.a0 = fp_sub(fp_mul(a.a0, b.a0), fp_mul(a.a1, b.a1));
+  r.a1 = fp_add(fp_mul(a.a0, b.a1), fp_mul(a.a1, b.a0));
+  return r;
+}
+inline Fp2 f2_inv(const Fp2& a) {
+  Fe4 d = fp_inv(fp_add(fp_mul(a.a0, a.a0), fp_mul(a.a1, a.a1)));
+  Fp2 r; r.a0 = fp_mul(a.a0, d); r.a1 = fp_neg(fp_mul(a.a1, d));
+  return r;
+}
+inline Fp2 f2_pow(const Fp2& a, const uint64_t e[4]) {
+  Fp2 acc = f2_one(), base = a;
+  for (int i = 0; i < 256; i++) {
+    if ((e[i / 64] >> (i % 64)) & 1) acc = f2_mul(acc, base);
+    base = f2_mul(base, base);
+  }
+  return acc;
+}
+// square root in Fp2 for p = 3 mod 4 (complex method); false if a is a non-residue
+inline bool f2_sqrt(const Fp2& a, Fp2* out) {
+  if (f2_is_zero(a)) { *out = a; return true; }
+  Fp2 a1 = f2_pow(a, EXP_P_MINUS3_DIV4);
+  Fp2 alpha = f2_mul(a1, f2_mul(a1, a));
+  Fp2 a0 = f2_mul(f2_conj(alpha), alpha);
+  Fp2 minus_one = f2_neg(f2_one());
+  if (f2_eq(a0, minus_one)) return false;
+  Fp2 x0 = f2_mul(a1, a);
+  Fp2 x;
+  if (f2_eq(alpha, minus_one)) {
+    x.a0 = fp_neg(x0.a1);  // i * x0
+    x.a1 = x0.a0;
+  } else {
+    Fp2 b = f2_pow(f2_add(f2_one(), alpha), EXP_P_MINUS1_DIV2);
+    x = f2_mul(b, x0);
+  }
+  if (!f2_eq(f2_mul(x, x), a)) return false;
+  *out = x;
+  return true;
+}
+
+struct G2 { Fp2 x, y; bool inf; };
+inline G2 g2_generator() {
+  G2 g;
+  g.x.a0 = fp_from_limbs(G2_X0); g.x.a1 = fp_from_limbs(G2_X1);
+  g.y.a0 = fp_from_limbs(G2_Y0); g.y.a1 = fp_from_limbs(G2_Y1);
+  g.inf = false;
+  return g;
+}
+inline Fp2 twist_b() { Fp2 b; b.a0 = fp_from_limbs(TWIST_B0); b.a1 = fp_from_limbs(TWIST_B1); return b; }
+inline G2 g2_add(const G2& a, const G2& b) {
+  if (a.inf) return b;
+  if (b.inf) return a;
+  Fp2 lam;
+  if (f2_eq(a.x, b.x)) {
+    if (f2_is_zero(f2_add(a.y, b.y))) { G2 r; r.x = r.y = f2_zero(); r.inf = true; return r; }
+    Fp2 xx = f2_mul(a.x, a.x);
+    lam = f2_mul(f2_add(f2_add(xx, xx), xx), f2_inv(f2_add(a.y, a.y)));
+  } else {
+    lam = f2_mul(f2_sub(b.y, a.y), f2_inv(f2_sub(b.x, a.x)));
+  }
+  G2 r;
+  r.x = f2_sub(f2_sub(f2_mul(lam, lam), a.x), b.x);
+  r.y = f2_sub(f2_mul(lam, f2_sub(a.x, r.x)), a.y);
+  r.inf = false;
+  return r;
+}
+inline G2 g2_mul(const G2& p, const Fe4& k_mont) {
+  Fe4 k = host::from_mont(HFR, k_mont);
+  G2 acc; acc.x = acc.y = f2_zero(); acc.inf = true;
+  for (int b = 255; b >= 0; b--) {
+    acc = g2_add(acc, acc);
+    if ((k.l[b / 64] >> (b % 64)) & 1) acc = g2_add(acc, p);
+  }
+  return acc;
+}
+// G2Affine.Bytes(): X.A1 || X.A0 (32-byte BE each), flags in the first byte; y sign: A1 decides unless it is zero
+inline bool f2_lex_largest(const Fp2& y) { return host::is_zero(y.a1) ? fp_lex_largest(y.a0) : fp_lex_largest(y.a1); }
+inline void g2_compress(const G2& p, uint8_t out[64]) {
+  if (p.inf) { memset(out, 0, 64); out[0] = 0x40; return; }
+  fp_to_be(p.x.a1, out);
+  fp_to_be(p.x.a0, out + 32);
+  out[0] |= f2_lex_largest(p.y) ? 0xC0 : 0x80;
+}
+inline bool g2_decompress(const uint8_t in[64], G2* out) {
+  const unsigned flag = in[0] >> 6;
+  if (flag == 1) { out->x = out->y = f2_zero(); out->inf = true; return true; }
+  if (flag == 0) return false;
+  uint8_t b[32];
+  memcpy(b, in, 32);
+  b[0] &= 0x3f;
+  bool ok1, ok0;
+  Fp2 x;
+  x.a1 = fp_from_be(b, &ok1);
+  x.a0 = fp_from_be(in + 32, &ok0);
+  if (!ok1 || !ok0) return false;
+  Fp2 rhs = f2_add(f2_mul(f2_mul(x, x), x), twist_b());
+  Fp2 y;
+  if (!f2_sqrt(rhs, &y)) return false;
+  if (f2_lex_largest(y) != (flag == 3)) y = f2_neg(y);
+  out->x = x; out->y = y; out->inf = false;
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------- Fp12 + pairing
+struct F12 { Fe4 c[12]; };
+inline F12 f12_zero() { F12 r; for (auto& x : r.c) x = fp_zero(); return r; }
+inline F12 f12_one() { F12 r = f12_zero(); r.c[0] = HFP.one; return r; }
+inline bool f12_eq(const F12& a, const F12& b) { for (int i = 0; i < 12; i++) if (!fe_eq(a.c[i], b.c[i])) return false; return true; }
+inline F12 f12_add(const F12& a, const F12& b) { F12 r; for (int i = 0; i < 12; i++) r.c[i] = fp_add(a.c[i], b.c[i]); return r; }
+inline F12 f12_sub(const F12& a, const F12& b) { F12 r; for (int i = 0; i < 12; i++) r.c[i] = fp_sub(a.c[i], b.c[i]); return r; }
+inline F12 f12_neg(const F12& a) { F12 r; for (int i = 0; i < 12; i++) r.c[i] = fp_neg(a.c[i]); return r; }
+inline F12 f12_scalar(const F12& a, uint64_t k) { Fe4 s = fp_small(k); F12 r; for (int i = 0; i < 12; i++) r.c[i] = fp_mul(a.c[i], s); return r; }
+inline F12 f12_mul(const F12& a, const F12& b) {
+  Fe4 t[23];
+  for (auto& x : t) x = fp_zero();
+  for (int i = 0; i < 12; i++) {
+    if (host::is_zero(a.c[i])) continue;
+    for (int j = 0; j < 12; j++) t[i + j] = fp_add(t[i + j], fp_mul(a.c[i], b.c[j]));
+  }
+  const Fe4 c18 = fp_small(18), c82 = fp_small(82);
+  for (int k = 22; k >= 12; k--) {  // w^12 = 18 w^6 - 82
+    if (host::is_zero(t[k])) continue;
+    t[k - 6] = fp_add(t[k - 6], fp_mul(t[k], c18));
+    t[k - 12] = fp_sub(t[k - 12], fp_mul(t[k], c82));
+  }
+  F12 r;
+  for (int i = 0; i < 12; i++) r.c[i] = t[i];
+  return r;
+}
+inline F12 f12_pow_limbs(const F12& a, const uint64_t* e, int nlimbs) {
+  F12 res = f12_one(), base = a;
+  for (int i = 0; i < nlimbs * 64; i++) {
+    if ((e[i / 64] >> (i % 64)) & 1) res = f12_mul(res, base);
+    base = f12_mul(base, base);
+  }
+  return res;
+}
+inline int poly_deg(const Fe4* p, int n) {
+  int d = n - 1;
+  while (d >= 0 && host::is_zero(p[d])) d--;
+  return d;
+}
+// inverse by the extended Euclidean algorithm in Fp[w] against w^12 - 18 w^6 + 82
+inline F12 f12_inv(const F12& a) {
+  Fe4 lm[13], hm[13], low[13], high[13];
+  for (int i = 0; i < 13; i++) { lm[i] = hm[i] = low[i] = high[i] = fp_zero(); }
+  lm[0] = HFP.one;
+  for (int i = 0; i < 12; i++) low[i] = a.c[i];
+  high[0] = fp_small(82);
+  high[6] = fp_neg(fp_small(18));
+  high[12] = HFP.one;
+  while (poly_deg(low, 13) > 0) {
+    const int dl = poly_deg(low, 13), dh = poly_deg(high, 13);
+    Fe4 quo[13], temp[13];
+    for (int i = 0; i < 13; i++) { quo[i] = fp_zero(); temp[i] = high[i]; }
+    const Fe4 inv_lead = fp_inv(low[dl]);
+    for (int i = dh - dl; i >= 0; i--) {
+      Fe4 q = fp_mul(temp[dl + i], inv_lead);
+      quo[i] = q;
+      for (int c = 0; c <= dl; c++) temp[c + i] = fp_sub(temp[c + i], fp_mul(low[c], q));
+    }
+    Fe4 nm[13], nw[13];
+    for (int i = 0; i < 13; i++) { nm[i] = hm[i]; nw[i] = high[i]; }
+    for (int i = 0; i < 13; i++)
+      for (int j = 0; j < 13 - i; j++) {
+        nm[i + j] = fp_sub(nm[i + j], fp_mul(lm[i], quo[j]));
+        nw[i + j] = fp_sub(nw[i + j], fp_mul(low[i], quo[j]));
+      }
+    for (int i = 0; i < 13; i++) { hm[i] = lm[i]; high[i] = low[i]; lm[i] = nm[i]; low[i] = nw[i]; }
+  }
+  const Fe4 inv0 = fp_inv(low[0]);
+  F12 r;
+  for (int i = 0; i < 12; i++) r.c[i] = fp_mul(lm[i], inv0);
+  return r;
+}
+// (c0 + c1 u) * w^shift, u = w^6 - 9
+inline F12 f12_from_f2(const Fp2& v, int shift) {
+  F12 r = f12_zero();
+  r.c[0] = fp_sub(v.a0, fp_mul(v.a1, fp_small(9)));
+  r.c[6] = v.a1;
+  if (shift) {
+    F12 wp = f12_zero();
+    wp.c[shift] = HFP.one;
+    r = f12_mul(r, wp);
+  }
+  return r;
+}
+struct E12 { F12 x, y; bool inf; };
+inline F12 e12_line(const E12& p1, const E12& p2, const E12& t) {
+  if (!f12_eq(p1.x, p2.x)) {
+    F12 m = f12_mul(f12_sub(p2.y, p1.y), f12_inv(f12_sub(p2.x, p1.x)));
+    return f12_sub(f12_mul(m, f12_sub(t.x, p1.x)), f12_sub(t.y, p1.y));
+  }
+  if (f12_eq(p1.y, p2.y)) {
+    F12 m = f12_mul(f12_scalar(f12_mul(p1.x, p1.x), 3), f12_inv(f12_scalar(p1.y, 2)));
+    return f12_sub(f12_mul(m, f12_sub(t.x, p1.x)), f12_sub(t.y, p1.y));
+  }
+  return f12_sub(t.x, p1.x);
+}
+inline E12 e12_add(const E12& p1, const E12& p2) {
+  if (p1.inf) return p2;
+  if (p2.inf) return p1;
+  F12 m;
+  if (f12_eq(p1.x, p2.x)) {
+    if (!f12_eq(p1.y, p2.y)) { E12 r; r.inf = true; r.x = r.y = f12_zero(); return r; }
+    m = f12_mul(f12_scalar(f12_mul(p1.x, p1.x), 3), f12_inv(f12_scalar(p1.y, 2)));
+  } else {
+    m = f12_mul(f12_sub(p2.y, p1.y), f12_inv(f12_sub(p2.x, p1.x)));
+  }
+  E12 r;
+  r.x = f12_sub(f12_sub(f12_mul(m, m), p1.x), p2.x);
+  r.y = f12_sub(f12_mul(m, f12_sub(p1.x, r.x)), p1.y);
+  r.inf = false;
+  return r;
+}
+inline F12 miller_loop(const G2& q, const G1& p) {
+  if (q.inf || p.inf) return f12_one();
+  E12 Q; Q.x = f12_from_f2(q.x, 2); Q.y = f12_from_f2(q.y, 3); Q.inf = false;
+  E12 P; P.x = f12_zero(); P.y = f12_zero(); P.x.c[0] = p.x; P.y.c[0] = p.y; P.inf = false;
+  E12 Rp = Q;
+  F12 f = f12_one();
+  // 6x+2 has 65 bits: bit 64 is the leading one, then ATE_LOOP_LO from bit 63 down
+  for (int i = 63; i >= 0; i--) {
+    f = f12_mul(f12_mul(f, f), e12_line(Rp, Rp, P));
+    Rp = e12_add(Rp, Rp);
+    if ((ATE_LOOP_LO >> i) & 1) {
+      f = f12_mul(f, e12_line(Rp, Q, P));
+      Rp = e12_add(Rp, Q);
+    }
+  }
+  E12 Q1; Q1.x = f12_pow_limbs(Q.x, P_LIMBS, 4); Q1.y = f12_pow_limbs(Q.y, P_LIMBS, 4); Q1.inf = false;
+  E12 nQ2; nQ2.x = f12_pow_limbs(Q1.x, P_LIMBS, 4); nQ2.y = f12_neg(f12_pow_limbs(Q1.y, P_LIMBS, 4)); nQ2.inf = false;
+  f = f12_mul(f, e12_line(Rp, Q1, P));
+  Rp = e12_add(Rp, Q1);
+  f = f12_mul(f, e12_line(Rp, nQ2, P));
+  return f;
+}
+// prod_i e(P_i, Q_i) == 1
+inline bool pairing_product_is_one(const std::vector<std::pair<G1, G2>>& pairs) {
+  F12 f = f12_one();
+  for (const auto& pq : pairs) f = f12_mul(f, miller_loop(pq.second, pq.first));
+  return f12_eq(f12_pow_limbs(f, FINAL_EXP, FINAL_EXP_LIMBS), f12_one());
+}
+
+}  // namespace ffi
+}  // namespace b200zk

@@ -45,6 +45,6 @@ def test_product_does_not_import_oracle():
     import pathlib
 
     pkg = pathlib.Path(zk.__file__).parent
-    for p in list(pkg.glob("*.py")) + list((pkg / "csrc").glob("*.cu*")):
+    for p in list(pkg.glob("*.py")) + list((pkg / "csrc").glob("*.cu*")) + list((pkg / "csrc").glob("*.h")) + list((pkg / "csrc" / "ffi").glob("*")):
         text = p.read_text()
         assert "oracle" not in text.lower(), p
