@@ -25,6 +25,8 @@ using namespace b200zk::ffi;
 
 namespace {
 
+#define TRACE(msg) do { if (getenv("B200ZK_FFI_TRACE")) { fprintf(stderr, "[ffi] %s:%d %s\n", __func__, __LINE__, msg); fflush(stderr); } } while (0)
+
 [[noreturn]] void fatal(const std::string& msg) {  // log.Fatal
   fprintf(stderr, "%s\n", msg.c_str());
   fflush(stderr);
@@ -412,6 +414,7 @@ void ensure_srs() {  // TryLoadSRS (common.go:127-144): the G2 pair (enough to v
 
 void ensure_srs_bases() {  // + the G1 powers resident in HBM, with the window table of the static bases
   ensure_srs();
+  TRACE("srs g2 ready");
   State& s = state();
   if (s.bases_ready) return;
   if (!s.bases) {
@@ -420,6 +423,7 @@ void ensure_srs_bases() {  // + the G1 powers resident in HBM, with the window t
     check(rc, "b200zk_bases_upload_compressed");
     std::vector<uint8_t>().swap(s.srs_file);
   }
+  TRACE("uploaded");
   b200zk_bases_precompute(context(), s.bases, 0);  // best effort: commitments use classic windows if memory is short
   s.bases_ready = true;
 }
@@ -430,6 +434,7 @@ b200zk_plonk_pk* setup_key(const R1CS& cs, const std::string& cache_key) {
   auto it = s.keys.find(cache_key);
   if (it != s.keys.end()) return it->second;
   ensure_srs_bases();
+  TRACE("bases ready");
   const size_t m = cs.gates.size();
   std::vector<Fe4> ql(m ? m : 1), qr(m ? m : 1), qm(m ? m : 1), qo(m ? m : 1), qk(m ? m : 1);
   std::vector<uint32_t> a(m ? m : 1), b(m ? m : 1), c(m ? m : 1);
@@ -632,12 +637,16 @@ extern "C" {
 struct PlonkPreprocess_return PlonkPreprocess(GoString acirJSON, GoString encodedRandomValues) {  // main.go:58-78
   const std::string acir = go_string(acirJSON);
   // the Rust side sends a JSON-quoted hex string (plonk/mod.rs:197-203); main.go:66-72 un-quotes it
-  JsonParser jp(go_string(encodedRandomValues));
+  const std::string quoted = go_string(encodedRandomValues);
+  JsonParser jp(quoted);
   Json q = jp.parse();
   if (!jp.ok || q.kind != Json::Str) fatal("json: cannot unmarshal encoded values into Go value of type string");
+  TRACE("parsed values");
   std::vector<Fe4> values = felts_from_hex(q.str);
   R1CS cs = build_sparse_r1cs(acir, values);
+  TRACE("built r1cs");
   b200zk_plonk_pk* pk = setup_key(cs, circuit_key(acir, values.size()));
+  TRACE("setup done");
   uint8_t vkp[8 * 64];
   check(b200zk_plonk_vk(context(), pk, vkp), "b200zk_plonk_vk");
   std::vector<uint8_t> vk = serialize_vk(cs, vkp);
