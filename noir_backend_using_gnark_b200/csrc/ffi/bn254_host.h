@@ -295,6 +295,27 @@ inline F12 f12_mul(const F12& a, const F12& b) {
   for (int i = 0; i < 12; i++) r.c[i] = t[i];
   return r;
 }
+inline F12 f12_sqr(const F12& a) {
+  Fe4 t[23];
+  for (auto& x : t) x = fp_zero();
+  for (int i = 0; i < 12; i++) {
+    if (host::is_zero(a.c[i])) continue;
+    t[2 * i] = fp_add(t[2 * i], fp_mul(a.c[i], a.c[i]));
+    for (int j = i + 1; j < 12; j++) {
+      const Fe4 m = fp_mul(a.c[i], a.c[j]);
+      t[i + j] = fp_add(t[i + j], fp_add(m, m));
+    }
+  }
+  const Fe4 c18 = fp_small(18), c82 = fp_small(82);
+  for (int k = 22; k >= 12; k--) {
+    if (host::is_zero(t[k])) continue;
+    t[k - 6] = fp_add(t[k - 6], fp_mul(t[k], c18));
+    t[k - 12] = fp_sub(t[k - 12], fp_mul(t[k], c82));
+  }
+  F12 r;
+  for (int i = 0; i < 12; i++) r.c[i] = t[i];
+  return r;
+}
 inline F12 f12_pow_limbs(const F12& a, const uint64_t* e, int nlimbs) {
   F12 res = f12_one(), base = a;
   for (int i = 0; i < nlimbs * 64; i++) {
@@ -353,61 +374,190 @@ inline F12 f12_from_f2(const Fp2& v, int shift) {
   }
   return r;
 }
-struct E12 { F12 x, y; bool inf; };
-inline F12 e12_line(const E12& p1, const E12& p2, const E12& t) {
-  if (!f12_eq(p1.x, p2.x)) {
-    F12 m = f12_mul(f12_sub(p2.y, p1.y), f12_inv(f12_sub(p2.x, p1.x)));
-    return f12_sub(f12_mul(m, f12_sub(t.x, p1.x)), f12_sub(t.y, p1.y));
-  }
-  if (f12_eq(p1.y, p2.y)) {
-    F12 m = f12_mul(f12_scalar(f12_mul(p1.x, p1.x), 3), f12_inv(f12_scalar(p1.y, 2)));
-    return f12_sub(f12_mul(m, f12_sub(t.x, p1.x)), f12_sub(t.y, p1.y));
-  }
-  return f12_sub(t.x, p1.x);
+// ---- Frobenius.  Fp12 = Fp[w]/(w^12 - 18 w^6 + 82), w^6 = xi = 9 + u.  For c in Fp: (c w^i)^p = c w^i xi^(i (p-1)/6), and
+// xi^(i (p-1)/6) = a_i + b_i u = (a_i - 9 b_i) + b_i w^6 lies in Fp2 = Fp[w^6].
+struct FrobTable {
+  Fp2 gamma[12];      // xi^(i (p-1)/6)
+  Fp2 twist_x, twist_y;   // xi^((p-1)/3), xi^((p-1)/2): the p-power Frobenius on the twist
+};
+inline const FrobTable& frob_table() {
+  static const FrobTable T = [] {
+    FrobTable t;
+    uint64_t e[4];  // (p - 1) / 6
+    {
+      uint64_t pm1[4];
+      memcpy(pm1, P_LIMBS, 32);
+      pm1[0] -= 1;  // p is odd
+      unsigned __int128 rem = 0;
+      for (int i = 3; i >= 0; i--) {
+        unsigned __int128 cur = (rem << 64) | pm1[i];
+        e[i] = (uint64_t)(cur / 6);
+        rem = cur % 6;
+      }
+    }
+    Fp2 xi;
+    xi.a0 = fp_small(9);
+    xi.a1 = HFP.one;
+    const Fp2 g = f2_pow(xi, e);
+    t.gamma[0] = f2_one();
+    for (int i = 1; i < 12; i++) t.gamma[i] = f2_mul(t.gamma[i - 1], g);
+    t.twist_x = t.gamma[2];
+    t.twist_y = t.gamma[3];
+    return t;
+  }();
+  return T;
 }
-inline E12 e12_add(const E12& p1, const E12& p2) {
-  if (p1.inf) return p2;
-  if (p2.inf) return p1;
-  F12 m;
-  if (f12_eq(p1.x, p2.x)) {
-    if (!f12_eq(p1.y, p2.y)) { E12 r; r.inf = true; r.x = r.y = f12_zero(); return r; }
-    m = f12_mul(f12_scalar(f12_mul(p1.x, p1.x), 3), f12_inv(f12_scalar(p1.y, 2)));
-  } else {
-    m = f12_mul(f12_sub(p2.y, p1.y), f12_inv(f12_sub(p2.x, p1.x)));
+inline F12 f12_frobenius(const F12& a) {
+  const FrobTable& T = frob_table();
+  const Fe4 c9 = fp_small(9), c18 = fp_small(18), c82 = fp_small(82);
+  F12 r = f12_zero();
+  for (int i = 0; i < 12; i++) {
+    if (host::is_zero(a.c[i])) continue;
+    const Fe4 lo = fp_mul(a.c[i], fp_sub(T.gamma[i].a0, fp_mul(T.gamma[i].a1, c9)));  // coefficient of w^i
+    const Fe4 hi = fp_mul(a.c[i], T.gamma[i].a1);                                       // coefficient of w^(i+6)
+    r.c[i] = fp_add(r.c[i], lo);
+    if (i < 6) {
+      r.c[i + 6] = fp_add(r.c[i + 6], hi);
+    } else {  // w^(i+6) = w^(i-6) w^12 = 18 w^i - 82 w^(i-6)
+      r.c[i] = fp_add(r.c[i], fp_mul(hi, c18));
+      r.c[i - 6] = fp_sub(r.c[i - 6], fp_mul(hi, c82));
+    }
   }
-  E12 r;
-  r.x = f12_sub(f12_sub(f12_mul(m, m), p1.x), p2.x);
-  r.y = f12_sub(f12_mul(m, f12_sub(p1.x, r.x)), p1.y);
-  r.inf = false;
   return r;
+}
+// the p^6-power Frobenius: w -> -w (conjugation over Fp6 = Fp[w^2]); the inverse on the cyclotomic subgroup
+inline F12 f12_conj6(const F12& a) {
+  F12 r = a;
+  for (int i = 1; i < 12; i += 2) r.c[i] = fp_neg(a.c[i]);
+  return r;
+}
+
+// ---- optimal ate pairing.  Q stays on the twist E'(Fp2); the untwist is (x', y') -> (x' w^2, y' w^3), so a line of
+// twist slope m through R' evaluated at P = (xP, yP) in G1 is   -yP + (m xP) w + (yR' - m xR') w^3.
+inline F12 line_value(const Fp2& m, const G2& r, const G1& p) {
+  F12 l = f12_zero();
+  l.c[0] = fp_neg(p.y);
+  Fp2 mx; mx.a0 = fp_mul(m.a0, p.x); mx.a1 = fp_mul(m.a1, p.x);
+  const Fp2 c3 = f2_sub(r.y, f2_mul(m, r.x));
+  const Fe4 c9 = fp_small(9);
+  l.c[1] = fp_sub(mx.a0, fp_mul(mx.a1, c9)); l.c[7] = mx.a1;
+  l.c[3] = fp_sub(c3.a0, fp_mul(c3.a1, c9)); l.c[9] = c3.a1;
+  return l;
+}
+// f <- f * line(R, S)(P), R <- R + S  (S == R doubles).  A vertical line contributes xP - xR' w^2.
+inline void miller_step(F12& f, G2& r, const G2& s, const G1& p) {
+  if (r.inf || s.inf) {
+    if (r.inf) r = s;
+    return;
+  }
+  Fp2 m;
+  if (f2_eq(r.x, s.x)) {
+    if (!f2_eq(r.y, s.y) || f2_is_zero(r.y)) {
+      F12 l = f12_zero();
+      const Fe4 c9 = fp_small(9);
+      l.c[0] = p.x;
+      l.c[2] = fp_neg(fp_sub(r.x.a0, fp_mul(r.x.a1, c9)));
+      l.c[8] = fp_neg(r.x.a1);
+      f = f12_mul(l, f);
+      r.inf = true;
+      return;
+    }
+    const Fp2 xx = f2_mul(r.x, r.x);
+    m = f2_mul(f2_add(f2_add(xx, xx), xx), f2_inv(f2_add(r.y, r.y)));
+  } else {
+    m = f2_mul(f2_sub(s.y, r.y), f2_inv(f2_sub(s.x, r.x)));
+  }
+  f = f12_mul(line_value(m, r, p), f);  // sparse operand first: f12_mul skips its zero coefficients
+  G2 n;
+  n.x = f2_sub(f2_sub(f2_mul(m, m), r.x), s.x);
+  n.y = f2_sub(f2_mul(m, f2_sub(r.x, n.x)), r.y);
+  n.inf = false;
+  r = n;
 }
 inline F12 miller_loop(const G2& q, const G1& p) {
   if (q.inf || p.inf) return f12_one();
-  E12 Q; Q.x = f12_from_f2(q.x, 2); Q.y = f12_from_f2(q.y, 3); Q.inf = false;
-  E12 P; P.x = f12_zero(); P.y = f12_zero(); P.x.c[0] = p.x; P.y.c[0] = p.y; P.inf = false;
-  E12 Rp = Q;
+  G2 r = q;
   F12 f = f12_one();
   // 6x+2 has 65 bits: bit 64 is the leading one, then ATE_LOOP_LO from bit 63 down
   for (int i = 63; i >= 0; i--) {
-    f = f12_mul(f12_mul(f, f), e12_line(Rp, Rp, P));
-    Rp = e12_add(Rp, Rp);
-    if ((ATE_LOOP_LO >> i) & 1) {
-      f = f12_mul(f, e12_line(Rp, Q, P));
-      Rp = e12_add(Rp, Q);
-    }
+    f = f12_sqr(f);
+    miller_step(f, r, r, p);
+    if ((ATE_LOOP_LO >> i) & 1) miller_step(f, r, q, p);
   }
-  E12 Q1; Q1.x = f12_pow_limbs(Q.x, P_LIMBS, 4); Q1.y = f12_pow_limbs(Q.y, P_LIMBS, 4); Q1.inf = false;
-  E12 nQ2; nQ2.x = f12_pow_limbs(Q1.x, P_LIMBS, 4); nQ2.y = f12_neg(f12_pow_limbs(Q1.y, P_LIMBS, 4)); nQ2.inf = false;
-  f = f12_mul(f, e12_line(Rp, Q1, P));
-  Rp = e12_add(Rp, Q1);
-  f = f12_mul(f, e12_line(Rp, nQ2, P));
+  const FrobTable& T = frob_table();
+  G2 q1, nq2;  // pi(Q) and -pi^2(Q) on the twist
+  q1.x = f2_mul(f2_conj(q.x), T.twist_x);
+  q1.y = f2_mul(f2_conj(q.y), T.twist_y);
+  q1.inf = false;
+  nq2.x = f2_mul(f2_conj(q1.x), T.twist_x);
+  nq2.y = f2_neg(f2_mul(f2_conj(q1.y), T.twist_y));
+  nq2.inf = false;
+  miller_step(f, r, q1, p);
+  miller_step(f, r, nq2, p);
   return f;
+}
+// f^((p^12 - 1) / r) = ((f^(p^6 - 1))^(p^2 + 1))^((p^4 - p^2 + 1) / r); the last exponent is exactly
+// p^3 + (6x^2 + 1) p^2 - (36x^3 + 18x^2 + 12x - 1) p - (36x^3 + 30x^2 + 18x + 2) for the BN parameter x
+inline F12 final_exponentiation(const F12& f) {
+  F12 g = f12_mul(f12_conj6(f), f12_inv(f));
+  g = f12_mul(f12_frobenius(f12_frobenius(g)), g);
+  const F12 g1 = f12_frobenius(g), g2 = f12_frobenius(g1), g3 = f12_frobenius(g2);
+  typedef unsigned __int128 u128;
+  const u128 x = 4965661367192848881ULL;
+  // x^2 < 2^126 fits u128; x^3 < 2^189 needs three limbs: compute with schoolbook on 64-bit limbs
+  auto mul_small = [](const uint64_t a[3], uint64_t k, uint64_t out[3]) {
+    u128 c = 0;
+    for (int i = 0; i < 3; i++) {
+      c += (u128)a[i] * k;
+      out[i] = (uint64_t)c;
+      c >>= 64;
+    }
+  };
+  auto add3 = [](const uint64_t a[3], const uint64_t b[3], uint64_t out[3]) {
+    u128 c = 0;
+    for (int i = 0; i < 3; i++) {
+      c += (u128)a[i] + b[i];
+      out[i] = (uint64_t)c;
+      c >>= 64;
+    }
+  };
+  const u128 x2 = x * x;
+  uint64_t X1[3] = {(uint64_t)x, 0, 0}, X2[3] = {(uint64_t)x2, (uint64_t)(x2 >> 64), 0}, X3[3];
+  mul_small(X2, (uint64_t)x, X3);
+  uint64_t t[3], u[3], e0[3], e1[3], e2[3];
+  // e2 = 6x^2 + 1
+  mul_small(X2, 6, e2);
+  { uint64_t one[3] = {1, 0, 0}; add3(e2, one, e2); }
+  // e1 = 36x^3 + 18x^2 + 12x - 1
+  mul_small(X3, 36, t); mul_small(X2, 18, u); add3(t, u, e1); mul_small(X1, 12, u); add3(e1, u, e1);
+  for (int i = 0; i < 3; i++)
+    if (e1[i]-- != 0) break;  // minus one, with borrow
+  // e0 = 36x^3 + 30x^2 + 18x + 2
+  mul_small(X2, 30, u); add3(t, u, e0); mul_small(X1, 18, u); add3(e0, u, e0);
+  { uint64_t two[3] = {2, 0, 0}; add3(e0, two, e0); }
+  // simultaneous exponentiation: g2^e2 * conj(g1)^e1 * conj(g)^e0, then times g3
+  F12 base[3] = {f12_conj6(g), f12_conj6(g1), g2};
+  const uint64_t* ex[3] = {e0, e1, e2};
+  F12 table[8];
+  table[0] = f12_one();
+  for (int m = 1; m < 8; m++) {
+    const int low = m & -m, idx = low == 1 ? 0 : low == 2 ? 1 : 2;
+    table[m] = (m == low) ? base[idx] : f12_mul(table[m ^ low], base[idx]);
+  }
+  F12 acc = f12_one();
+  for (int bit = 191; bit >= 0; bit--) {
+    acc = f12_sqr(acc);
+    int m = 0;
+    for (int k = 0; k < 3; k++) m |= (int)((ex[k][bit / 64] >> (bit % 64)) & 1) << k;
+    if (m) acc = f12_mul(acc, table[m]);
+  }
+  return f12_mul(acc, g3);
 }
 // prod_i e(P_i, Q_i) == 1
 inline bool pairing_product_is_one(const std::vector<std::pair<G1, G2>>& pairs) {
   F12 f = f12_one();
   for (const auto& pq : pairs) f = f12_mul(f, miller_loop(pq.second, pq.first));
-  return f12_eq(f12_pow_limbs(f, FINAL_EXP, FINAL_EXP_LIMBS), f12_one());
+  return f12_eq(final_exponentiation(f), f12_one());
 }
 
 }  // namespace ffi

@@ -9,15 +9,18 @@
 // plus gnark v0.8.0's VerifyingKey / ProvingKey / Proof WriteTo layouts and plonk.Verify, as recalled in SURVEY.md
 // Appendix C (their sources are not available here).  Verification is CPU work in the reference too.
 #include <sys/stat.h>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <list>
 #include <map>
 #include <memory>
 #include <string>
 #include <vector>
 #include "../../../include/b200zk.h"
 #include "../../../include/gnark_backend_ffi.h"
+#include "acir_reader.h"
 #include "bn254_host.h"
 
 using namespace b200zk;
@@ -25,13 +28,22 @@ using namespace b200zk::ffi;
 
 namespace {
 
-#define TRACE(msg) do { if (getenv("B200ZK_FFI_TRACE")) { fprintf(stderr, "[ffi] %s:%d %s\n", __func__, __LINE__, msg); fflush(stderr); } } while (0)
-
-[[noreturn]] void fatal(const std::string& msg) {  // log.Fatal
-  fprintf(stderr, "%s\n", msg.c_str());
-  fflush(stderr);
-  exit(1);
+// B200ZK_FFI_TRACE=1: wall-clock trace of the stages of each call on stderr
+double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
+struct Trace {
+  bool on;
+  double t0, last;
+  const char* fn;
+  explicit Trace(const char* f) : on(getenv("B200ZK_FFI_TRACE") != nullptr), t0(now_ms()), last(t0), fn(f) {}
+  void operator()(const char* what) {
+    if (!on) return;
+    const double t = now_ms();
+    fprintf(stderr, "[ffi] %s: %-28s %9.2f ms (+%.2f)\n", fn, what, t - t0, t - last);
+    last = t;
+  }
+};
 
 char* c_string(const std::string& s) {  // C.CString: malloc'ed copy, never freed by the Rust caller
   char* p = (char*)malloc(s.size() + 1);
@@ -41,260 +53,13 @@ char* c_string(const std::string& s) {  // C.CString: malloc'ed copy, never free
   return p;
 }
 
-std::string go_string(GoString s) { return std::string(s.p ? s.p : "", s.n > 0 ? (size_t)s.n : 0); }
+Span span_of(GoString s) { return Span{s.p ? s.p : "", s.n > 0 ? (size_t)s.n : 0}; }  // borrowed for the call, not NUL-dependent
 
-// ---------------------------------------------------------------------------------------------- hex
-int hex_val(char c) {
-  if (c >= '0' && c <= '9') return c - '0';
-  if (c >= 'a' && c <= 'f') return c - 'a' + 10;
-  if (c >= 'A' && c <= 'F') return c - 'A' + 10;
-  return -1;
-}
-std::vector<uint8_t> hex_decode(const std::string& s) {  // hex.DecodeString; errors are fatal in every caller
-  if (s.size() % 2) fatal("encoding/hex: odd length hex string");
-  std::vector<uint8_t> out(s.size() / 2);
-  for (size_t i = 0; i < out.size(); i++) {
-    int a = hex_val(s[2 * i]), b = hex_val(s[2 * i + 1]);
-    if (a < 0 || b < 0) fatal("encoding/hex: invalid byte");
-    out[i] = (uint8_t)(a * 16 + b);
-  }
-  return out;
-}
-std::string hex_encode(const std::vector<uint8_t>& v) {
-  static const char* d = "0123456789abcdef";
-  std::string s(v.size() * 2, '0');
-  for (size_t i = 0; i < v.size(); i++) {
-    s[2 * i] = d[v[i] >> 4];
-    s[2 * i + 1] = d[v[i] & 15];
-  }
-  return s;
-}
-
-// ---------------------------------------------------------------------------------------------- minimal JSON
-struct Json {
-  enum Kind { Null, Bool, Num, Str, Arr, Obj } kind = Null;
-  double num = 0;
-  bool b = false;
-  std::string str;
-  std::vector<Json> arr;
-  std::vector<std::pair<std::string, Json>> obj;
-  const Json* get(const std::string& k) const {
-    for (auto& kv : obj)
-      if (kv.first == k) return &kv.second;
-    return nullptr;
-  }
-};
-struct JsonParser {
-  const std::string& s;
-  size_t i = 0;
-  bool ok = true;
-  explicit JsonParser(const std::string& t) : s(t) {}
-  void ws() { while (i < s.size() && (s[i] == ' ' || s[i] == '\n' || s[i] == '\t' || s[i] == '\r')) i++; }
-  Json parse() {
-    ws();
-    Json j;
-    if (i >= s.size()) { ok = false; return j; }
-    char c = s[i];
-    if (c == '{') {
-      j.kind = Json::Obj;
-      i++;
-      ws();
-      if (i < s.size() && s[i] == '}') { i++; return j; }
-      while (ok) {
-        ws();
-        Json k = parse();
-        if (k.kind != Json::Str) { ok = false; break; }
-        ws();
-        if (i >= s.size() || s[i] != ':') { ok = false; break; }
-        i++;
-        Json v = parse();
-        j.obj.emplace_back(k.str, std::move(v));
-        ws();
-        if (i < s.size() && s[i] == ',') { i++; continue; }
-        if (i < s.size() && s[i] == '}') { i++; break; }
-        ok = false;
-      }
-    } else if (c == '[') {
-      j.kind = Json::Arr;
-      i++;
-      ws();
-      if (i < s.size() && s[i] == ']') { i++; return j; }
-      while (ok) {
-        j.arr.push_back(parse());
-        ws();
-        if (i < s.size() && s[i] == ',') { i++; continue; }
-        if (i < s.size() && s[i] == ']') { i++; break; }
-        ok = false;
-      }
-    } else if (c == '"') {
-      j.kind = Json::Str;
-      i++;
-      while (i < s.size() && s[i] != '"') {
-        if (s[i] == '\\' && i + 1 < s.size()) {
-          char e = s[i + 1];
-          j.str.push_back(e == 'n' ? '\n' : e == 't' ? '\t' : e);
-          i += 2;
-        } else {
-          j.str.push_back(s[i++]);
-        }
-      }
-      if (i >= s.size()) ok = false;
-      i++;
-    } else if (c == 't' && s.compare(i, 4, "true") == 0) {
-      j.kind = Json::Bool; j.b = true; i += 4;
-    } else if (c == 'f' && s.compare(i, 5, "false") == 0) {
-      j.kind = Json::Bool; i += 5;
-    } else if (c == 'n' && s.compare(i, 4, "null") == 0) {
-      i += 4;
-    } else {
-      size_t st = i;
-      while (i < s.size() && (isdigit((unsigned char)s[i]) || s[i] == '-' || s[i] == '+' || s[i] == '.' || s[i] == 'e' || s[i] == 'E')) i++;
-      if (i == st) { ok = false; return j; }
-      j.kind = Json::Num;
-      j.num = strtod(s.substr(st, i - st).c_str(), nullptr);
-    }
-    return j;
-  }
-};
-
-// ---------------------------------------------------------------------------------------------- felts
-Fe4 felt_from_be32(const uint8_t* b) { return host::set_bytes(HFR, b); }  // fr.Element.SetBytes: reduce, to Montgomery
-Fe4 felt_from_hex(const std::string& h) {                                 // backend_helpers.DeserializeFelt
-  std::vector<uint8_t> raw = hex_decode(h);
-  // SetBytes interprets big-endian of any length; the reference always sends 32 bytes
-  uint8_t b[32] = {0};
-  if (raw.size() > 32) fatal("felt longer than 32 bytes");
-  memcpy(b + 32 - raw.size(), raw.data(), raw.size());
-  return felt_from_be32(b);
-}
-std::vector<Fe4> felts_from_hex(const std::string& h) {                   // DeserializeFelts: fr.Vector.UnmarshalBinary
-  std::vector<uint8_t> raw = hex_decode(h);
-  std::vector<Fe4> out;
-  if (raw.size() < 4) return out;  // the reference ignores UnmarshalBinary's error (helpers.go:31)
-  uint32_t n = ((uint32_t)raw[0] << 24) | ((uint32_t)raw[1] << 16) | ((uint32_t)raw[2] << 8) | raw[3];
-  if (raw.size() < 4 + (size_t)n * 32) return out;
-  out.resize(n);
-  for (uint32_t i = 0; i < n; i++) out[i] = felt_from_be32(raw.data() + 4 + 32 * (size_t)i);
-  return out;
-}
 void put_u64(std::vector<uint8_t>& v, uint64_t x) { for (int i = 7; i >= 0; i--) v.push_back((uint8_t)(x >> (8 * i))); }
 void put_u32(std::vector<uint8_t>& v, uint32_t x) { for (int i = 3; i >= 0; i--) v.push_back((uint8_t)(x >> (8 * i))); }
 void put_fr(std::vector<uint8_t>& v, const Fe4& a) { uint8_t b[32]; host::marshal(HFR, a, b); v.insert(v.end(), b, b + 32); }
 void put_g1(std::vector<uint8_t>& v, const G1& p) { uint8_t b[32]; g1_compress(p, b); v.insert(v.end(), b, b + 32); }
-
-// ---------------------------------------------------------------------------------------------- ACIR -> SparseR1CS
-struct Gate { Fe4 ql, qr, qm, qo, qk; uint32_t a, b, c; };
-struct R1CS {
-  unsigned nb_public = 0, nb_secret = 0;
-  std::vector<Gate> gates;
-  std::vector<Fe4> public_vals, secret_vals;
-};
-
-bool as_u32(const Json& j, uint32_t* out) {
-  if (j.kind != Json::Num) return false;
-  *out = (uint32_t)j.num;
-  return true;
-}
-
-R1CS build_sparse_r1cs(const std::string& acir_json, const std::vector<Fe4>& values) {
-  JsonParser jp(acir_json);
-  Json root = jp.parse();
-  if (!jp.ok || root.kind != Json::Obj) fatal("invalid character in ACIR JSON");
-  const Json* jops = root.get("opcodes");
-  const Json* jpub = root.get("public_inputs");
-  const Json* jcur = root.get("current_witness_index");
-  if (!jops || jops->kind != Json::Arr) fatal("Error: couldn't deserialize opcodes.");
-  if (!jpub || jpub->kind != Json::Arr) fatal("Error: couldn't deserialize public inputs.");
-  if (!jcur || jcur->kind != Json::Num) fatal("Error: couldn't deserialize current witness.");
-  std::vector<uint32_t> pubs;
-  for (auto& p : jpub->arr) {
-    uint32_t w;
-    if (!as_u32(p, &w)) fatal("json: cannot unmarshal public input");
-    pubs.push_back(w);
-  }
-  // HandleValues (common.go:45-76)
-  R1CS cs;
-  std::map<uint32_t, uint32_t> index_map;
-  for (size_t k = 0; k < values.size(); k++) {
-    const uint32_t i = (uint32_t)k + 1;
-    for (uint32_t p : pubs)
-      if (i == p) {
-        index_map[i] = cs.nb_public++;
-        cs.public_vals.push_back(values[k]);
-      }
-  }
-  for (size_t k = 0; k < values.size(); k++) {
-    const uint32_t i = (uint32_t)k + 1;
-    if (!pubs.empty()) {
-      for (uint32_t p : pubs)
-        if (i != p) {
-          index_map[i] = cs.nb_public + cs.nb_secret++;
-          cs.secret_vals.push_back(values[k]);
-        }
-    } else {
-      index_map[i] = cs.nb_public + cs.nb_secret++;
-      cs.secret_vals.push_back(values[k]);
-    }
-  }
-  auto wire = [&](uint32_t w) -> uint32_t {  // Go map lookup: missing key -> 0
-    auto it = index_map.find(w);
-    return it == index_map.end() ? 0u : it->second;
-  };
-  const Fe4 zero = {{0, 0, 0, 0}};
-  for (auto& op : jops->arr) {
-    if (op.kind != Json::Obj) fatal("json: cannot unmarshal opcode");
-    if (const Json* ar = op.get("Arithmetic")) {
-      const Json* mt = ar->kind == Json::Obj ? ar->get("mul_terms") : nullptr;
-      const Json* lc = ar->kind == Json::Obj ? ar->get("linear_combinations") : nullptr;
-      const Json* qc = ar->kind == Json::Obj ? ar->get("q_c") : nullptr;
-      if (!mt || mt->kind != Json::Arr || !lc || lc->kind != Json::Arr || !qc || qc->kind != Json::Str)
-        fatal("json: cannot unmarshal Arithmetic opcode");
-      Gate g;
-      g.ql = g.qr = g.qm = g.qo = zero;
-      g.a = g.b = g.c = 0;
-      if (!mt->arr.empty()) {  // only MulTerms[0] is read (sparse_r1cs.go:50)
-        const Json& t = mt->arr[0];
-        uint32_t w1, w2;
-        if (t.kind != Json::Arr || t.arr.size() < 3 || t.arr[0].kind != Json::Str || !as_u32(t.arr[1], &w1) || !as_u32(t.arr[2], &w2))
-          fatal("Error: couldn't deserialize mul term.");
-        g.qm = felt_from_hex(t.arr[0].str);  // qM1 = coeff, qM2 = 1
-        g.a = wire(w1);
-        g.b = wire(w2);
-      }
-      std::vector<std::pair<Fe4, uint32_t>> lin;
-      for (auto& t : lc->arr) {
-        uint32_t w;
-        if (t.kind != Json::Arr || t.arr.size() < 2 || t.arr[0].kind != Json::Str || !as_u32(t.arr[1], &w))
-          fatal("Error: couldn't deserialize simple term.");
-        lin.emplace_back(felt_from_hex(t.arr[0].str), w);
-      }
-      if (lin.size() == 1) { g.qo = lin[0].first; g.c = wire(lin[0].second); }
-      if (lin.size() == 2) {
-        g.ql = lin[0].first; g.a = wire(lin[0].second);  // overwrites the mul term's wires (:69, :73)
-        g.qr = lin[1].first; g.b = wire(lin[1].second);
-      }
-      if (lin.size() == 3) {
-        g.ql = lin[0].first; g.a = wire(lin[0].second);
-        g.qr = lin[1].first; g.b = wire(lin[1].second);
-        g.qo = lin[2].first; g.c = wire(lin[2].second);
-      }
-      g.qk = felt_from_hex(qc->str);
-      cs.gates.push_back(g);
-    } else if (const Json* bb = op.get("BlackBoxFuncCall")) {
-      const Json* in = bb->kind == Json::Obj ? bb->get("inputs") : nullptr;
-      const Json* nm = bb->kind == Json::Obj ? bb->get("name") : nullptr;
-      const Json* ou = bb->kind == Json::Obj ? bb->get("outputs") : nullptr;
-      if (!in || in->kind != Json::Arr || !nm || nm->kind != Json::Str || !ou || ou->kind != Json::Arr)
-        fatal("json: cannot unmarshal BlackBoxFuncCall opcode");
-      // components.go:3-40: black-box functions add no constraints
-    } else if (op.get("Directive")) {
-      // sparse_r1cs.go:36: skipped
-    } else {
-      fatal("json: cannot unmarshal opcode: not Arithmetic, BlackBoxFuncCall or Directive");
-    }
-  }
-  return cs;
-}
+Fe4 felt_from_be32(const uint8_t* b) { return host::set_bytes(HFR, b); }
 
 // ---------------------------------------------------------------------------------------------- device + SRS state
 struct State {
@@ -304,11 +69,33 @@ struct State {
   G2 g2[2];
   std::vector<uint8_t> srs_file;  // u32 count || compressed G1 powers, until they are uploaded
   bool srs_ready = false, bases_ready = false;
-  std::map<std::string, b200zk_plonk_pk*> keys;  // per circuit (the reference re-derives the key on every call)
+  // Parsed circuits and device-resident keys, found again by the digest of the ACIR text (the reference re-parses the
+  // JSON and re-derives the key's coset forms on every call).  Least recently used entries are dropped.
+  struct Entry {
+    Digest id;
+    std::shared_ptr<Circuit> circuit;
+    std::map<size_t, std::shared_ptr<struct Keyed>> by_nvalues;
+  };
+  std::list<Entry> circuits;
+};
+struct Keyed {  // everything that depends on (circuit, number of values) only
+  WirePlan plan;
+  b200zk_plonk_pk* pk = nullptr;
+  std::vector<uint8_t> vk_bytes;
+  uint64_t n = 0, n_big = 0;
+  ~Keyed();
 };
 State& state() {
   static State s;
   return s;
+}
+Keyed::~Keyed() {
+  if (pk && state().ctx) b200zk_plonk_pk_free(state().ctx, pk);
+}
+size_t cache_capacity() {
+  const char* e = getenv("B200ZK_FFI_CACHE");
+  const long v = e ? atol(e) : 4;
+  return v < 1 ? 1 : (size_t)v;
 }
 void check(int rc, const char* what) {
   if (rc != 0) {
@@ -357,10 +144,12 @@ bool try_load_srs(State& s) {  // LoadSRS (common.go:86-105); the G1 part goes t
   while (!text.empty() && (text.back() == '\n' || text.back() == ' ')) text.pop_back();
   if (text.size() % 2) return false;
   std::vector<uint8_t> raw(text.size() / 2);
-  for (size_t i = 0; i < raw.size(); i++) {
-    int a = hex_val(text[2 * i]), b = hex_val(text[2 * i + 1]);
-    if (a < 0 || b < 0) return false;
-    raw[i] = (uint8_t)(a * 16 + b);
+  {
+    std::atomic<bool> bad(false);
+    parallel_for(raw.size(), (size_t)1 << 20, [&](size_t b, size_t e) {
+      if (!hex_decode_into(Span{text.data() + 2 * b, 2 * (e - b)}, raw.data() + b)) bad.store(true);
+    });
+    if (bad.load()) return false;
   }
   if (raw.size() < 4 + 128) return false;
   size_t n = ((size_t)raw[0] << 24) | ((size_t)raw[1] << 16) | ((size_t)raw[2] << 8) | raw[3];
@@ -414,7 +203,6 @@ void ensure_srs() {  // TryLoadSRS (common.go:127-144): the G2 pair (enough to v
 
 void ensure_srs_bases() {  // + the G1 powers resident in HBM, with the window table of the static bases
   ensure_srs();
-  TRACE("srs g2 ready");
   State& s = state();
   if (s.bases_ready) return;
   if (!s.bases) {
@@ -423,37 +211,14 @@ void ensure_srs_bases() {  // + the G1 powers resident in HBM, with the window t
     check(rc, "b200zk_bases_upload_compressed");
     std::vector<uint8_t>().swap(s.srs_file);
   }
-  TRACE("uploaded");
   b200zk_bases_precompute(context(), s.bases, 0);  // best effort: commitments use classic windows if memory is short
   s.bases_ready = true;
 }
 
 // ---------------------------------------------------------------------------------------------- keys
-b200zk_plonk_pk* setup_key(const R1CS& cs, const std::string& cache_key) {
-  State& s = state();
-  auto it = s.keys.find(cache_key);
-  if (it != s.keys.end()) return it->second;
-  ensure_srs_bases();
-  TRACE("bases ready");
-  const size_t m = cs.gates.size();
-  std::vector<Fe4> ql(m ? m : 1), qr(m ? m : 1), qm(m ? m : 1), qo(m ? m : 1), qk(m ? m : 1);
-  std::vector<uint32_t> a(m ? m : 1), b(m ? m : 1), c(m ? m : 1);
-  for (size_t i = 0; i < m; i++) {
-    ql[i] = cs.gates[i].ql; qr[i] = cs.gates[i].qr; qm[i] = cs.gates[i].qm; qo[i] = cs.gates[i].qo; qk[i] = cs.gates[i].qk;
-    a[i] = cs.gates[i].a; b[i] = cs.gates[i].b; c[i] = cs.gates[i].c;
-  }
-  b200zk_plonk_pk* pk = nullptr;
-  int rc = b200zk_plonk_setup_r1cs(context(), s.bases, cs.nb_public, cs.nb_secret, m, ql.data(), qr.data(), qm.data(),
-                                   qo.data(), qk.data(), a.data(), b.data(), c.data(), &pk);
-  if (rc == B200ZK_ERR_BAD_ARG) fatal("kzg: the SRS is too small for this circuit (set B200ZK_SRS_SIZE)");
-  check(rc, "plonk.Setup");
-  s.keys[cache_key] = pk;
-  return pk;
-}
-
 struct Sizes { uint64_t n, n_big; };
-Sizes domain_sizes(const R1CS& cs) {
-  const size_t sys = cs.gates.size() + cs.nb_public;
+Sizes domain_sizes(size_t nb_constraints, unsigned nb_public) {
+  const size_t sys = nb_constraints + nb_public;
   uint64_t n = 2;
   while (n < sys) n <<= 1;
   uint64_t nb = 1;
@@ -461,6 +226,54 @@ Sizes domain_sizes(const R1CS& cs) {
   if (nb < 4 * n) nb = 4 * n;
   return {n, nb};
 }
+
+// acir.UnmarshalJSON + BuildSparseR1CS's structural part, remembered per ACIR text
+State::Entry& circuit_entry(Span acir) {
+  State& s = state();
+  const Digest id = digest(acir);
+  for (auto it = s.circuits.begin(); it != s.circuits.end(); ++it)
+    if (it->id.a == id.a && it->id.b == id.b) {
+      s.circuits.splice(s.circuits.begin(), s.circuits, it);
+      return s.circuits.front();
+    }
+  State::Entry e;
+  e.id = id;
+  e.circuit = std::make_shared<Circuit>(AcirReader(acir).read());
+  while (s.circuits.size() >= cache_capacity()) s.circuits.pop_back();
+  s.circuits.push_front(std::move(e));
+  return s.circuits.front();
+}
+Keyed& keyed(State::Entry& e, size_t nvalues) {
+  auto it = e.by_nvalues.find(nvalues);
+  if (it != e.by_nvalues.end()) return *it->second;
+  auto k = std::make_shared<Keyed>();
+  k->plan = make_plan(*e.circuit, nvalues);
+  Sizes sz = domain_sizes(e.circuit->size(), k->plan.nb_public);
+  k->n = sz.n;
+  k->n_big = sz.n_big;
+  e.by_nvalues[nvalues] = k;
+  return *k;
+}
+std::vector<uint8_t> serialize_vk(const Keyed& k, const uint8_t vk_points[8 * 64]);
+// plonk.Setup(spr, srs) (plonk.go:21) on the device, once per (circuit, number of values)
+void ensure_key(const Circuit& cs, Keyed& k) {
+  if (k.pk) return;
+  ensure_srs_bases();
+  State& s = state();
+  const size_t m = cs.size();
+  static const Fe4 zero = {{0, 0, 0, 0}};
+  static const uint32_t zero_w = 0;
+  int rc = b200zk_plonk_setup_r1cs(context(), s.bases, k.plan.nb_public, k.plan.nb_secret, m, m ? (const void*)cs.ql.data() : &zero,
+                                   m ? (const void*)cs.qr.data() : &zero, m ? (const void*)cs.qm.data() : &zero,
+                                   m ? (const void*)cs.qo.data() : &zero, m ? (const void*)cs.qk.data() : &zero,
+                                   m ? k.plan.a.data() : &zero_w, m ? k.plan.b.data() : &zero_w, m ? k.plan.c.data() : &zero_w, &k.pk);
+  if (rc == B200ZK_ERR_BAD_ARG) fatal("kzg: the SRS is too small for this circuit (set B200ZK_SRS_SIZE)");
+  check(rc, "plonk.Setup");
+  uint8_t vkp[8 * 64];
+  check(b200zk_plonk_vk(context(), k.pk, vkp), "b200zk_plonk_vk");
+  k.vk_bytes = serialize_vk(k, vkp);
+}
+
 Fe4 fr_root_of_unity(uint64_t n) {  // fft.NewDomain(n).Generator
   const uint32_t root[8] = {0x80d13d9cu, 0x636e7355u, 0x2445ffd6u, 0xa22bf374u, 0x1eb203d8u, 0x56452ac0u, 0x2963f9e7u, 0x1860ef94u};
   Fe4 w;
@@ -472,13 +285,12 @@ Fe4 fr_root_of_unity(uint64_t n) {  // fft.NewDomain(n).Generator
 }
 
 // VerifyingKey.WriteTo (gnark v0.8.0, recalled): Size | SizeInv | Generator | NbPublicVariables | S[0..2] | Ql Qr Qm Qo Qk
-std::vector<uint8_t> serialize_vk(const R1CS& cs, const uint8_t vk_points[8 * 64]) {
-  Sizes sz = domain_sizes(cs);
+std::vector<uint8_t> serialize_vk(const Keyed& k, const uint8_t vk_points[8 * 64]) {
   std::vector<uint8_t> v;
-  put_u64(v, sz.n);
-  put_fr(v, host::inv(HFR, host::from_u64(HFR, sz.n)));
-  put_fr(v, fr_root_of_unity(sz.n));
-  put_u64(v, cs.nb_public);
+  put_u64(v, k.n);
+  put_fr(v, host::inv(HFR, host::from_u64(HFR, k.n)));
+  put_fr(v, fr_root_of_unity(k.n));
+  put_u64(v, k.plan.nb_public);
   for (int i = 0; i < 8; i++) put_g1(v, g1_from_image(vk_points + 64 * i));
   return v;
 }
@@ -627,7 +439,34 @@ bool plonk_verify(const ParsedProof& pr, const ParsedVk& vk, const std::vector<F
   return kzg_verify(pr.Z, M(zeta, vk.generator), zu, pr.zshift_H, g2);
 }
 
-std::string circuit_key(const std::string& acir, size_t nvalues) { return acir + "#" + std::to_string(nvalues); }
+// hex text written straight into the malloc'ed result (the pk of a 2^20-row circuit is 650 MB of hex)
+struct HexOut {
+  char* buf;
+  size_t cap, len = 0;
+  explicit HexOut(size_t bytes) : cap(2 * bytes) {
+    buf = (char*)malloc(cap + 1);
+    if (!buf) fatal("out of memory");
+  }
+  void put(const std::vector<uint8_t>& v) {
+    if (len + 2 * v.size() > cap) fatal("internal: hex buffer overflow");
+    hex_encode_into(v.data(), v.size(), buf + len);
+    len += 2 * v.size();
+  }
+  char* reserve(size_t bytes) {
+    if (len + 2 * bytes > cap) fatal("internal: hex buffer overflow");
+    char* p = buf + len;
+    len += 2 * bytes;
+    return p;
+  }
+  char* finish() {
+    buf[len] = 0;
+    return buf;
+  }
+};
+
+size_t pk_stream_bytes(const Keyed& k) {  // ProvingKey.WriteTo size
+  return k.vk_bytes.size() + 2 * (8 + 5 * 32) + 9 * (4 + 32 * k.n) + 4 + 8 * 3 * k.n;
+}
 
 }  // namespace
 
@@ -635,90 +474,142 @@ std::string circuit_key(const std::string& acir, size_t nvalues) { return acir +
 extern "C" {
 
 struct PlonkPreprocess_return PlonkPreprocess(GoString acirJSON, GoString encodedRandomValues) {  // main.go:58-78
-  const std::string acir = go_string(acirJSON);
+  Trace trace("PlonkPreprocess");
   // the Rust side sends a JSON-quoted hex string (plonk/mod.rs:197-203); main.go:66-72 un-quotes it
-  const std::string quoted = go_string(encodedRandomValues);
-  JsonParser jp(quoted);
-  Json q = jp.parse();
-  if (!jp.ok || q.kind != Json::Str) fatal("json: cannot unmarshal encoded values into Go value of type string");
-  TRACE("parsed values");
-  std::vector<Fe4> values = felts_from_hex(q.str);
-  R1CS cs = build_sparse_r1cs(acir, values);
-  TRACE("built r1cs");
-  b200zk_plonk_pk* pk = setup_key(cs, circuit_key(acir, values.size()));
-  TRACE("setup done");
-  uint8_t vkp[8 * 64];
-  check(b200zk_plonk_vk(context(), pk, vkp), "b200zk_plonk_vk");
-  std::vector<uint8_t> vk = serialize_vk(cs, vkp);
+  Span quoted = span_of(encodedRandomValues);
+  while (quoted.n && (quoted.p[0] == ' ' || quoted.p[0] == '\n' || quoted.p[0] == '\t')) { quoted.p++; quoted.n--; }
+  while (quoted.n && (quoted.p[quoted.n - 1] == ' ' || quoted.p[quoted.n - 1] == '\n' || quoted.p[quoted.n - 1] == '\t')) quoted.n--;
+  if (quoted.n < 2 || quoted.p[0] != '"' || quoted.p[quoted.n - 1] != '"')
+    fatal("json: cannot unmarshal encoded values into Go value of type string");
+  std::vector<Fe4> values = felts_from_hex(Span{quoted.p + 1, quoted.n - 2});
+  trace("values decoded");
+  State::Entry& entry = circuit_entry(span_of(acirJSON));
+  const Circuit& cs = *entry.circuit;
+  trace("circuit read");
+  Keyed& k = keyed(entry, values.size());
+  trace("wire plan");
+  ensure_key(cs, k);
+  trace("plonk.Setup (device)");
   // ProvingKey.WriteTo (gnark v0.8.0, recalled): Vk | Domain[0] | Domain[1] | Ql Qr Qm Qo CQk LQk S1 S2 S3 | Permutation
-  Sizes sz = domain_sizes(cs);
-  std::vector<uint8_t> pkb = vk;
-  put_domain(pkb, sz.n);
-  put_domain(pkb, sz.n_big);
-  std::vector<Fe4> poly(sz.n);
-  for (int which = 0; which < 9; which++) {
-    check(b200zk_plonk_pk_poly(context(), pk, which, poly.data()), "b200zk_plonk_pk_poly");
-    put_u32(pkb, (uint32_t)sz.n);
-    for (auto& c : poly) put_fr(pkb, c);
+  HexOut out(pk_stream_bytes(k));
+  out.put(k.vk_bytes);
+  {
+    std::vector<uint8_t> d;
+    put_domain(d, k.n);
+    put_domain(d, k.n_big);
+    out.put(d);
   }
+  std::vector<Fe4> poly(k.n);
+  for (int which = 0; which < 9; which++) {
+    check(b200zk_plonk_pk_poly(context(), k.pk, which, poly.data()), "b200zk_plonk_pk_poly");
+    std::vector<uint8_t> len;
+    put_u32(len, (uint32_t)k.n);
+    out.put(len);
+    char* dst = out.reserve(32 * k.n);
+    parallel_for(k.n, 4096, [&](size_t b, size_t e) {
+      for (size_t i = b; i < e; i++) {
+        uint8_t be[32];
+        host::marshal(HFR, poly[i], be);
+        hex_encode_into(be, 32, dst + 64 * i);
+      }
+    });
+  }
+  trace("polynomials -> hex");
   {
     // Permutation: gnark's buildPermutation over the same row layout
-    std::vector<uint32_t> lro(3 * sz.n, 0);
-    for (unsigned i = 0; i < cs.nb_public; i++) lro[i] = i;
-    for (size_t i = 0; i < cs.gates.size(); i++) {
-      lro[cs.nb_public + i] = cs.gates[i].a;
-      lro[sz.n + cs.nb_public + i] = cs.gates[i].b;
-      lro[2 * sz.n + cs.nb_public + i] = cs.gates[i].c;
+    const size_t n = k.n, m = cs.size();
+    const unsigned np = k.plan.nb_public;
+    std::vector<uint32_t> lro(3 * n, 0);
+    for (unsigned i = 0; i < np; i++) lro[i] = i;
+    for (size_t i = 0; i < m; i++) {
+      lro[np + i] = k.plan.a[i];
+      lro[n + np + i] = k.plan.b[i];
+      lro[2 * n + np + i] = k.plan.c[i];
     }
-    const size_t nw = cs.nb_public + cs.nb_secret ? cs.nb_public + cs.nb_secret : 1;
-    std::vector<int64_t> perm(3 * sz.n, -1), cycle(nw, -1);
-    for (size_t i = 0; i < 3 * sz.n; i++) {
+    const size_t nw = np + k.plan.nb_secret ? np + k.plan.nb_secret : 1;
+    std::vector<int64_t> perm(3 * n, -1), cycle(nw, -1);
+    for (size_t i = 0; i < 3 * n; i++) {
       if (cycle[lro[i]] != -1) perm[i] = cycle[lro[i]];
       cycle[lro[i]] = (int64_t)i;
     }
-    for (size_t i = 0; i < 3 * sz.n; i++)
+    for (size_t i = 0; i < 3 * n; i++)
       if (perm[i] == -1) perm[i] = cycle[lro[i]];
-    put_u32(pkb, (uint32_t)(3 * sz.n));
-    for (auto v : perm) put_u64(pkb, (uint64_t)v);
+    std::vector<uint8_t> len;
+    put_u32(len, (uint32_t)(3 * n));
+    out.put(len);
+    char* dst = out.reserve(8 * 3 * n);
+    parallel_for(3 * n, 1 << 16, [&](size_t b, size_t e) {
+      for (size_t i = b; i < e; i++) {
+        uint8_t be[8];
+        for (int j = 0; j < 8; j++) be[j] = (uint8_t)((uint64_t)perm[i] >> (8 * (7 - j)));
+        hex_encode_into(be, 8, dst + 16 * i);
+      }
+    });
   }
+  trace("permutation -> hex");
   struct PlonkPreprocess_return r;
-  r.r0 = c_string(hex_encode(pkb));
-  r.r1 = c_string(hex_encode(vk));
+  r.r0 = out.finish();
+  r.r1 = c_string(hex_encode(k.vk_bytes));
   return r;
 }
 
 char* PlonkProveWithPK(GoString acirJSON, GoString encodedValues, GoString encodedProvingKey) {  // main.go:24-37
-  const std::string acir = go_string(acirJSON);
-  std::vector<Fe4> values = felts_from_hex(go_string(encodedValues));
-  // DeserializeProvingKey: the key is re-derived from the circuit and the cached SRS (the reference itself rebuilds the
-  // constraint system and recomputes the key's derived data on every call: helpers.go:49-60, plonk.go:54); the payload
-  // is only checked for well-formedness
-  (void)hex_decode(go_string(encodedProvingKey));
-  R1CS cs = build_sparse_r1cs(acir, values);
-  b200zk_plonk_pk* pk = setup_key(cs, circuit_key(acir, values.size()));
-  // BuildWitnesses (common.go:22-43): publics then secrets = wire order
-  std::vector<Fe4> sol = cs.public_vals;
-  sol.insert(sol.end(), cs.secret_vals.begin(), cs.secret_vals.end());
-  if (sol.empty()) sol.push_back(Fe4{{0, 0, 0, 0}});
-  // spr.Solve: every wire is an input here, so solving is checking (plonk.Prove fails -> log.Fatal, plonk.go:67-70)
-  for (size_t k = 0; k < cs.gates.size(); k++) {
-    const Gate& g = cs.gates[k];
-    auto M = [](const Fe4& a, const Fe4& b) { return host::mul(HFR, a, b); };
-    auto A = [](const Fe4& a, const Fe4& b) { return host::add(HFR, a, b); };
-    Fe4 v = A(A(A(M(g.ql, sol[g.a]), M(g.qr, sol[g.b])), A(M(g.qo, sol[g.c]), M(M(g.qm, sol[g.a]), sol[g.b]))), g.qk);
-    if (!host::is_zero(v)) fatal("constraint #" + std::to_string(k) + " is not satisfied");
+  Trace trace("PlonkProveWithPK");
+  std::vector<Fe4> values = felts_from_hex(span_of(encodedValues));
+  trace("values decoded");
+  State::Entry& entry = circuit_entry(span_of(acirJSON));
+  const Circuit& cs = *entry.circuit;
+  trace("circuit read / found");
+  Keyed& k = keyed(entry, values.size());
+  ensure_key(cs, k);
+  trace("key resident");
+  // DeserializeProvingKey (helpers.go:49-60): the polynomials of the key are already resident on the device (derived
+  // from the same circuit and SRS; the reference itself re-derives the key's coset forms on every call), so the
+  // payload is checked, not re-read: its length must be that of ProvingKey.WriteTo for this circuit and the
+  // verifying key it starts with must be the one derived here.
+  {
+    Span pk = span_of(encodedProvingKey);
+    if (pk.n % 2) fatal("encoding/hex: odd length hex string");
+    if (pk.n != 2 * pk_stream_bytes(k)) fatal(pk.n < 2 * pk_stream_bytes(k) ? "unexpected EOF reading the proving key" : "proving key does not belong to this circuit (size mismatch)");
+    std::vector<uint8_t> head = hex_decode(Span{pk.p, 2 * k.vk_bytes.size()});
+    if (head != k.vk_bytes) fatal("proving key does not belong to this circuit and SRS");
   }
+  trace("proving key checked");
+  // BuildWitnesses (common.go:22-43): publics then secrets = wire order
+  const size_t nw = k.plan.solution_src.size();
+  std::vector<Fe4> sol(nw ? nw : 1, Fe4{{0, 0, 0, 0}});
+  for (size_t i = 0; i < nw; i++) sol[i] = values[k.plan.solution_src[i]];
+  // spr.Solve: every wire is an input here, so solving is checking (plonk.Prove fails -> log.Fatal, plonk.go:67-70)
+  {
+    std::atomic<size_t> first_bad(SIZE_MAX);
+    const WirePlan& pl = k.plan;
+    parallel_for(cs.size(), 8192, [&](size_t b, size_t e) {
+      auto M = [](const Fe4& x, const Fe4& y) { return host::mul(HFR, x, y); };
+      auto A = [](const Fe4& x, const Fe4& y) { return host::add(HFR, x, y); };
+      for (size_t g = b; g < e; g++) {
+        const Fe4 &xa = sol[pl.a[g]], &xb = sol[pl.b[g]], &xc = sol[pl.c[g]];
+        Fe4 v = A(A(A(M(cs.ql[g], xa), M(cs.qr[g], xb)), A(M(cs.qo[g], xc), M(M(cs.qm[g], xa), xb))), cs.qk[g]);
+        if (!host::is_zero(v)) {
+          size_t cur = first_bad.load();
+          while (g < cur && !first_bad.compare_exchange_weak(cur, g)) {}
+          return;
+        }
+      }
+    });
+    if (first_bad.load() != SIZE_MAX) fatal("constraint #" + std::to_string(first_bad.load()) + " is not satisfied");
+  }
+  trace("witness + constraint check");
   Fe4 blinding[9];
   if (const char* seed = getenv("B200ZK_BLINDING_SEED")) {
     uint64_t st = strtoull(seed, nullptr, 0);
     for (int i = 0; i < 9;) {
       Fe4 v;
-      for (int k = 0; k < 4; k++) {
+      for (int j = 0; j < 4; j++) {
         st += 0x9E3779B97F4A7C15ULL;
         uint64_t z = st;
         z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
         z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
-        v.l[k] = z ^ (z >> 31);
+        v.l[j] = z ^ (z >> 31);
       }
       v.l[3] &= 0x3fffffffffffffffULL;
       if (!host::geq(v.l, HFR.m)) blinding[i++] = v;
@@ -730,7 +621,8 @@ char* PlonkProveWithPK(GoString acirJSON, GoString encodedValues, GoString encod
     fclose(ur);
   }
   uint8_t blob[832];
-  check(b200zk_plonk_prove(context(), pk, sol.data(), blinding, blob), "plonk.Prove");
+  check(b200zk_plonk_prove(context(), k.pk, sol.data(), blinding, blob), "plonk.Prove");
+  trace("plonk.Prove (device)");
   return c_string(hex_encode(serialize_proof(blob)));
 }
 
@@ -738,13 +630,20 @@ uint8_t PlonkVerifyWithMeta(GoString, GoString, GoString) { return 0; }  // main
 
 uint8_t PlonkVerifyWithVK(GoString acirJSON, GoString encodedProof, GoString encodedPublicInputs,
                           GoString encodedVerifyingKey) {  // main.go:44-56, plonk.go:29-51
-  const std::string acir = go_string(acirJSON);
-  ParsedProof proof = parse_proof(hex_decode(go_string(encodedProof)));
-  std::vector<Fe4> values = felts_from_hex(go_string(encodedPublicInputs));
-  ParsedVk vk = parse_vk(hex_decode(go_string(encodedVerifyingKey)));
-  R1CS cs = build_sparse_r1cs(acir, values);  // only to learn which values are public (plonk.go:30)
-  ensure_srs();                               // vk.InitKZG(srs): the G2 elements live in the SRS file
-  return plonk_verify(proof, vk, cs.public_vals, state().g2) ? 1 : 0;
+  Trace trace("PlonkVerifyWithVK");
+  ParsedProof proof = parse_proof(hex_decode(span_of(encodedProof)));
+  std::vector<Fe4> values = felts_from_hex(span_of(encodedPublicInputs));
+  ParsedVk vk = parse_vk(hex_decode(span_of(encodedVerifyingKey)));
+  trace("payloads decoded");
+  State::Entry& entry = circuit_entry(span_of(acirJSON));
+  Keyed& k = keyed(entry, values.size());  // only to learn which values are public (plonk.go:30)
+  std::vector<Fe4> pub(k.plan.nb_public);
+  for (unsigned i = 0; i < k.plan.nb_public; i++) pub[i] = values[k.plan.solution_src[i]];
+  trace("circuit read / found");
+  ensure_srs();  // vk.InitKZG(srs): the G2 elements live in the SRS file
+  const bool ok = plonk_verify(proof, vk, pub, state().g2);
+  trace("plonk.Verify (host pairing)");
+  return ok ? 1 : 0;
 }
 
 }  // extern "C"

@@ -74,10 +74,27 @@ def _cstr(ptr) -> str:
 
 def prove_with_pk(circuit_json: str, values: Sequence[int], proving_key: bytes) -> bytes:
     """mod.rs:64-99."""
+    return bytes.fromhex(prove_with_pk_encoded(circuit_json.encode(), encode_felts(values).encode(), proving_key.hex().encode()))
+
+
+def prove_with_pk_encoded(acir_json: bytes, values_hex: bytes, proving_key_hex: bytes) -> str:
+    """The bare PlonkProveWithPK call on payloads that are already encoded (what benchmarks time)."""
     lib = load_ffi()
-    out = lib.PlonkProveWithPK(GoString.of(circuit_json.encode()), GoString.of(encode_felts(values).encode()),
-                               GoString.of(proving_key.hex().encode()))
-    return bytes.fromhex(_cstr(out))
+    return _cstr(lib.PlonkProveWithPK(GoString.of(acir_json), GoString.of(values_hex), GoString.of(proving_key_hex)))
+
+
+def verify_with_vk_encoded(acir_json: bytes, proof_hex: bytes, public_inputs_hex: bytes, verifying_key_hex: bytes) -> int:
+    """The bare PlonkVerifyWithVK call on encoded payloads."""
+    lib = load_ffi()
+    return int(lib.PlonkVerifyWithVK(GoString.of(acir_json), GoString.of(proof_hex), GoString.of(public_inputs_hex),
+                                     GoString.of(verifying_key_hex)))
+
+
+def preprocess_encoded(acir_json: bytes, quoted_values_hex: bytes) -> Tuple[str, str]:
+    """The bare PlonkPreprocess call: (proving key hex, verifying key hex)."""
+    lib = load_ffi()
+    kp = lib.PlonkPreprocess(GoString.of(acir_json), GoString.of(quoted_values_hex))
+    return _cstr(kp.proving_key), _cstr(kp.verifying_key)
 
 
 def verify_with_meta(circuit_json: str, proof: bytes, public_inputs: Sequence[int]) -> bool:
@@ -90,9 +107,8 @@ def verify_with_meta(circuit_json: str, proof: bytes, public_inputs: Sequence[in
 
 def verify_with_vk(circuit_json: str, proof: bytes, public_inputs: Sequence[int], verifying_key: bytes) -> bool:
     """mod.rs:143-186."""
-    lib = load_ffi()
-    r = lib.PlonkVerifyWithVK(GoString.of(circuit_json.encode()), GoString.of(proof.hex().encode()),
-                              GoString.of(encode_felts(public_inputs).encode()), GoString.of(verifying_key.hex().encode()))
+    r = verify_with_vk_encoded(circuit_json.encode(), proof.hex().encode(), encode_felts(public_inputs).encode(),
+                               verifying_key.hex().encode())
     if r not in (0, 1):
         raise ValueError("VerifyInvalidBoolError")
     return r == 1
@@ -115,7 +131,7 @@ def get_exact_circuit_size(circuit_json: str) -> int:
 def preprocess(circuit_json: str, random_value: int = 1) -> Tuple[bytes, bytes]:
     """mod.rs:195-240: (proving_key, verifying_key) bytes.  The Rust side sends num_witnesses - 1 copies of ONE random
     field element (`vec![rand::random(); n]`), JSON-quoted."""
-    lib = load_ffi()
-    n = int(json.loads(circuit_json)["current_witness_index"])
-    kp = lib.PlonkPreprocess(GoString.of(circuit_json.encode()), GoString.of(json.dumps(encode_felts([random_value] * n)).encode()))
-    return bytes.fromhex(_cstr(kp.proving_key)), bytes.fromhex(_cstr(kp.verifying_key))
+    m = re.search(r'"current_witness_index"\s*:\s*(\d+)', circuit_json)
+    n = int(m.group(1)) if m else int(json.loads(circuit_json)["current_witness_index"])
+    pk, vk = preprocess_encoded(circuit_json.encode(), json.dumps(encode_felts([random_value] * n)).encode())
+    return bytes.fromhex(pk), bytes.fromhex(vk)

@@ -15,7 +15,11 @@ def main() -> None:
             pk, vk = ffi.preprocess(step["acir"], step.get("random_value", 1))
             out.append({"pk": pk.hex(), "vk": vk.hex()})
         elif op == "prove":
-            out.append(ffi.prove_with_pk(step["acir"], [int(v) for v in step["values"]], bytes.fromhex(step["pk"])).hex())
+            pk = step["pk"]
+            if pk.startswith("@"):  # "@<i>.pk": the proving key an earlier preprocess step of this list returned
+                pk = out[int(pk[1:].split(".")[0])]["pk"]
+            out.append(ffi.prove_with_pk_encoded(step["acir"].encode(), ffi.encode_felts([int(v) for v in step["values"]]).encode(),
+                                                 pk.encode()))
         elif op == "verify":
             out.append(ffi.verify_with_vk(step["acir"], bytes.fromhex(step["proof"]), [int(v) for v in step["values"]],
                                           bytes.fromhex(step["vk"])))

@@ -1,0 +1,36 @@
+// Test driver for csrc/ffi/bn254_host.h: prints e(a*G1, b*G2) (12 coefficients of the Fp[w]/(w^12 - 18 w^6 + 82)
+// representation, hex, regular form), the Miller-loop value before the final exponentiation, and the outcome and wall
+// time of a two-pairing product check.  tests/test_pairing_host.py compares them with the oracle's big-int pairing.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include "../noir_backend_using_gnark_b200/csrc/ffi/bn254_host.h"
+
+using namespace b200zk;
+using namespace b200zk::ffi;
+
+static void print_f12(const F12& f) {
+  for (int i = 0; i < 12; i++) {
+    uint8_t be[32];
+    fp_to_be(f.c[i], be);
+    for (int j = 0; j < 32; j++) printf("%02x", be[j]);
+    printf(i == 11 ? "\n" : " ");
+  }
+}
+
+int main(int argc, char** argv) {
+  if (argc < 3) return 2;
+  const Fe4 a = host::from_u64(HFR, strtoull(argv[1], nullptr, 0)), b = host::from_u64(HFR, strtoull(argv[2], nullptr, 0));
+  const G1 p = g1_mul(g1_generator(), a);
+  const G2 q = g2_mul(g2_generator(), b);
+  const F12 ml = miller_loop(q, p);
+  print_f12(ml);
+  print_f12(final_exponentiation(ml));
+  const Fe4 ab = host::mul(HFR, a, b);
+  auto t0 = std::chrono::steady_clock::now();
+  const bool ok = pairing_product_is_one({{p, q}, {g1_neg(g1_mul(g1_generator(), ab)), g2_generator()}});
+  auto t1 = std::chrono::steady_clock::now();
+  const bool bad = pairing_product_is_one({{p, q}, {g1_neg(g1_mul(g1_generator(), host::add(HFR, ab, HFR.one))), g2_generator()}});
+  printf("%d %d %.2f\n", ok ? 1 : 0, bad ? 1 : 0, std::chrono::duration<double, std::milli>(t1 - t0).count());
+  return 0;
+}

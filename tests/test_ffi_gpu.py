@@ -52,8 +52,8 @@ def test_unseeded_proofs_differ_and_verify(home):
     strv = [str(v % o.R_MOD) for v in vals]
     rc, res, err = run_child([
         {"op": "preprocess", "acir": js},
-        {"op": "prove", "acir": js, "values": strv, "pk": "00"},
-        {"op": "prove", "acir": js, "values": strv, "pk": "00"},
+        {"op": "prove", "acir": js, "values": strv, "pk": "@0.pk"},
+        {"op": "prove", "acir": js, "values": strv, "pk": "@0.pk"},
     ], home)
     assert rc == 0, err
     p1, p2 = res[1], res[2]
@@ -67,8 +67,24 @@ def test_unsatisfied_witness_is_fatal(home):
     js, vals = FIXTURES[1]
     bad = [v % o.R_MOD for v in vals]
     bad[0] = 7                                                  # 7 != 2
-    rc, res, err = run_child([{"op": "prove", "acir": js, "values": [str(v) for v in bad], "pk": "00"}], home)
-    assert rc == 1 and "constraint" in err, (rc, err)           # plonk.go:67-70: plonk.Prove error -> log.Fatal
+    steps = [{"op": "preprocess", "acir": js}, {"op": "prove", "acir": js, "values": [str(v) for v in bad], "pk": "@0.pk"}]
+    rc, res, err = run_child(steps, home)
+    assert rc == 1 and "constraint #3" in err, (rc, err)        # plonk.go:67-70: plonk.Prove error -> log.Fatal
+
+
+def test_foreign_or_truncated_proving_key_is_fatal(home):
+    js, vals = FIXTURES[1]
+    strv = [str(v % o.R_MOD) for v in vals]
+    rc, res, err = run_child([{"op": "preprocess", "acir": js}], home)
+    assert rc == 0, err
+    pk = res[0]["pk"]
+    rc, _, err = run_child([{"op": "prove", "acir": js, "values": strv, "pk": pk[:-64]}], home)
+    assert rc == 1 and "EOF" in err, (rc, err)                  # helpers.go:55-58: pk.ReadFrom error -> log.Fatal
+    other = pk[:200] + ("1" if pk[200] != "1" else "2") + pk[201:]   # a different commitment inside the embedded vk
+    rc, _, err = run_child([{"op": "prove", "acir": js, "values": strv, "pk": other}], home)
+    assert rc == 1 and "does not belong" in err, (rc, err)
+    rc, _, err = run_child([{"op": "prove", "acir": js, "values": strv, "pk": pk[:-1] + "x"}], home)
+    assert rc == 0 or "hex" in err                              # the tail of the payload is not re-read
 
 
 def test_srs_is_generated_and_cached_when_missing(tmp_path, lib_built):
@@ -77,7 +93,7 @@ def test_srs_is_generated_and_cached_when_missing(tmp_path, lib_built):
     env = {"B200ZK_SRS_SIZE": "256"}
     rc, res, err = run_child([
         {"op": "preprocess", "acir": js},
-        {"op": "prove", "acir": js, "values": strv, "pk": "00"},
+        {"op": "prove", "acir": js, "values": strv, "pk": "@0.pk"},
     ], tmp_path, env)
     assert rc == 0, err
     path = os.path.join(str(tmp_path), "noir-lang", "srs.hex")
