@@ -435,6 +435,21 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
             dist.destroy_process_group()
         return
 
+    # ---- rank 0 only: the same prover through the reference's own string FFI (include/gnark_backend_ffi.h), in a
+    # child process because the FFI library keeps its own SRS / key state and reads $XDG_CONFIG_HOME
+    ffi_info = None
+    if not args.no_prove and world == 1:
+        import subprocess
+
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ffi_bench.py"), "16", "3"], capture_output=True,
+                               text=True, timeout=300)
+            ffi_info = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else {"error": r.stderr[-300:]}
+            ffi_info["api"] = ("PlonkPreprocess / PlonkProveWithPK / PlonkVerifyWithVK (GoString payloads: ACIR JSON, hex felts, "
+                               "hex keys) on a 2^16-row ACIR circuit; wall clock per call")
+        except Exception as e:  # the headline numbers do not depend on this leg
+            ffi_info = {"error": repr(e)}
+
     # ---- rank 0 only: roofline denominators, NTT figures, CPU baseline
     imad_peak = ctx.microbench(0)
     fpmul_peak = ctx.microbench(1)
@@ -519,6 +534,7 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
         "phase_share": phase_share,
         "ntt": ntt_info,
         "plonk_prove": prove_info,
+        "string_ffi": ffi_info,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)

@@ -69,7 +69,7 @@ def test_unsatisfied_witness_is_fatal(home):
     bad[0] = 7                                                  # 7 != 2
     steps = [{"op": "preprocess", "acir": js}, {"op": "prove", "acir": js, "values": [str(v) for v in bad], "pk": "@0.pk"}]
     rc, res, err = run_child(steps, home)
-    assert rc == 1 and "constraint #3" in err, (rc, err)        # plonk.go:67-70: plonk.Prove error -> log.Fatal
+    assert rc == 1 and "constraint #0" in err, (rc, err)        # plonk.go:67-70: plonk.Prove error -> log.Fatal
 
 
 def test_foreign_or_truncated_proving_key_is_fatal(home):
