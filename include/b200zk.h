@@ -135,6 +135,9 @@ int b200zk_g1_sum_dev(b200zk_ctx* ctx, const void* partials_dev, size_t count, v
 int b200zk_msm_set_flat_scatter(b200zk_ctx* ctx, int on);
 /* force the Pippenger window size (0 = choose from n); for tests and tuning */
 int b200zk_msm_set_window(b200zk_ctx* ctx, int c);
+/* measurement: the number of windows (= bucket additions per point) an MSM of n points of these bases will use
+ * (12 with the window table at 2^24 points, ceil(255/c) classic windows otherwise); < 0 = error code */
+int b200zk_msm_windows(const b200zk_ctx* ctx, const b200zk_bases* bases, size_t n);
 
 
 /* ---- device-resident PLONK prover ----------------------------------------------------------------------

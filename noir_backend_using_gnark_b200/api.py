@@ -225,6 +225,13 @@ class SRS:
         _lib.check(self.ctx.handle, self.ctx.lib.b200zk_bases_precompute(self.ctx.handle, self.handle, int(c)))
         return self
 
+    def windows(self, n: Optional[int] = None) -> int:
+        """Bucket additions per point an MSM of n of these bases performs (measurement aid)."""
+        w = self.ctx.lib.b200zk_msm_windows(self.ctx.handle, self.handle, self.n if n is None else n)
+        if w < 0:
+            _lib.check(self.ctx.handle, w)
+        return w
+
     def download(self, first: int = 0, n: Optional[int] = None) -> bytes:
         n = self.n - first if n is None else n
         out = np.zeros(max(n, 1) * 64, dtype=np.uint8)

@@ -412,6 +412,11 @@ int b200zk_msm_set_flat_scatter(b200zk_ctx* ctx, int on) {
   return B200ZK_OK;
 }
 
+int b200zk_msm_windows(const b200zk_ctx* ctx, const b200zk_bases* bases, size_t n) {
+  if (!ctx || !bases || n == 0 || n > bases->n) return B200ZK_ERR_BAD_ARG;
+  return (int)msm_window_count(ctx, bases, n);
+}
+
 int b200zk_msm_set_window(b200zk_ctx* ctx, int c) {
   if (!ctx || (c != 0 && (c < 6 || c > 16))) return B200ZK_ERR_BAD_ARG;
   ctx->forced_window = c;

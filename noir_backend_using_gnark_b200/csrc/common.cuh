@@ -154,6 +154,7 @@ int ntt_prepare(b200zk_ctx* ctx, unsigned log2n);  // builds the twiddle / coset
 int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const void* scalars_dev, size_t n,
             void* out_dev, int out_kind);
 int msm_precompute_run(b200zk_ctx* ctx, b200zk_bases* bases, int c);
+unsigned msm_window_count(const b200zk_ctx* ctx, const b200zk_bases* bases, size_t n);
 int g1_sum_run(b200zk_ctx* ctx, const void* partials_dev, size_t count, void* out_affine_dev);
 int srs_decompress_run(b200zk_ctx* ctx, const void* compressed_host, size_t n, void* out_dev, unsigned* bad_count);
 int srs_compress_run(b200zk_ctx* ctx, const void* points_dev, size_t n, void* out_host);

@@ -641,6 +641,15 @@ int msm_precompute_run(b200zk_ctx* ctx, b200zk_bases* bases, int c_req) {
   return B200ZK_OK;
 }
 
+// number of windows (= bucket additions per point) msm_run uses for n points of these bases; same rule as below
+unsigned msm_window_count(const b200zk_ctx* ctx, const b200zk_bases* bases, size_t n) {
+  if (bases->table && !ctx->forced_window && n * 16 >= bases->n) return bases->tab_W;
+  unsigned c = ctx->forced_window ? (unsigned)ctx->forced_window : choose_window(n);
+  if (c < 6) c = 6;
+  if (c > 16) c = 16;
+  return (255 + c - 1) / c;
+}
+
 int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const void* scalars_dev, size_t n,
             void* out_dev, int out_kind) {
   if (!bases || !out_dev || (n && !scalars_dev)) return B200ZK_ERR_BAD_ARG;
