@@ -274,6 +274,10 @@ def run_prove(ctx, log2n: int, rank: int = 0, world: int = 1, cpu_sample_log2: i
                                  c["lro"], ctx)
     setup_ms = (time.perf_counter() - t0) * 1e3
     blind = random_fr_images(9, 0xB2000006)
+    import torch
+
+    sol_pinned = torch.from_numpy(c["sol"]).pin_memory()   # the caller's host buffer, page-locked (b200zk_host_alloc for C hosts)
+    c["sol"] = sol_pinned.numpy()
 
     def timed():
         pk.Prove(c["sol"], blind)  # warm-up

@@ -35,7 +35,8 @@ typedef enum b200zk_error {
   B200ZK_ERR_CUDA = -2,        /* a CUDA runtime call failed; see b200zk_last_cuda_error */
   B200ZK_ERR_BAD_ARG = -3,     /* null pointer, log2n > 28, n > bases, ... */
   B200ZK_ERR_OOM = -4,         /* device allocation failed */
-  B200ZK_ERR_UNSUPPORTED = -5
+  B200ZK_ERR_UNSUPPORTED = -5,
+  B200ZK_ERR_UNSATISFIED = -6  /* b200zk_plonk_prove: the solution violates a constraint (what spr.Solve reports) */
 } b200zk_error;
 
 enum { B200ZK_DIF = 0, B200ZK_DIT = 1 };
@@ -87,6 +88,10 @@ int b200zk_dev_free(b200zk_ctx* ctx, void* p);
 int b200zk_ipc_export(b200zk_ctx* ctx, void* dev_ptr, void* handle_out_64);
 int b200zk_ipc_import(b200zk_ctx* ctx, const void* handle_64, void** out);
 int b200zk_ipc_close(b200zk_ctx* ctx, void* imported);
+/* page-locked host buffers for callers without a CUDA runtime of their own (the Go / C++ host side): host arguments
+ * of the *_host entry points living in such a buffer are copied by DMA at PCIe speed instead of being staged */
+int b200zk_host_alloc(b200zk_ctx* ctx, size_t bytes, void** out);
+int b200zk_host_free(b200zk_ctx* ctx, void* p);
 /* tests / tuning: force the plain radix-2 pass kernel instead of the radix-4 register kernel (same results) */
 int b200zk_ntt_set_radix2(b200zk_ctx* ctx, int on);
 /* fft.BitReverse(a): in-place index bit-reversal permutation. */
@@ -157,6 +162,9 @@ int b200zk_msm_windows(const b200zk_ctx* ctx, const b200zk_bases* bases, size_t 
  *   blinding = the 9 fr.SetRandom draws in gnark's order L,L,R,R,O,O,Z,Z,Z (their limbs are the Montgomery form).
  *   proof_out (832 B) = LRO[0..2], Z, H[0..2], BatchedProof.H, ZShiftedOpening.H as G1Affine (64 B each), then
  *   BatchedProof.ClaimedValues[0..6] and ZShiftedOpening.ClaimedValue as fr.Element (32 B each).
+ *   Like plonk.Prove (whose spr.Solve fails first), it refuses a solution that violates a constraint: every row is
+ *   checked on the device and B200ZK_ERR_UNSATISFIED is returned; b200zk_plonk_unsatisfied_row then gives the first
+ *   failing row (row - nb_public = index of the constraint), -1 after a successful prove.
  * Must be called with the context the key was set up on. */
 typedef struct b200zk_plonk_pk b200zk_plonk_pk;
 /* Commitment hook: when set, every kzg.Commit inside b200zk_plonk_prove calls fn(user, scalars_dev, n, out_dev)
@@ -183,6 +191,7 @@ int b200zk_plonk_vk(b200zk_ctx* ctx, const b200zk_plonk_pk* pk, void* out_8_poin
 int b200zk_plonk_pk_poly(b200zk_ctx* ctx, const b200zk_plonk_pk* pk, int which, void* out_host);
 int b200zk_plonk_prove(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solution_host, const void* blinding_host,
                        void* proof_out);
+long long b200zk_plonk_unsatisfied_row(const b200zk_plonk_pk* pk);
 
 /* ---- measurement ----------------------------------------------------------------------------------------
  * Integer-pipe microbenchmarks used as roofline denominators (synchronous).  which = 0: IMAD.WIDE.U32 multiply-

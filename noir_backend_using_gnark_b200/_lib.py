@@ -11,6 +11,7 @@ LIB_PATH = PKG / "lib" / "libb200zk.so"
 HEADER = PKG.parent / "include" / "b200zk.h"
 
 DIF, DIT = 0, 1
+ERR_UNSATISFIED = -6
 MAX_LOG2N = 28
 
 
@@ -63,6 +64,8 @@ def load() -> C.CDLL:
         "b200zk_ntt_dist_half0_p2p_dev": (i, [vp, vp, C.POINTER(vp), u, u, u, u, i, i, i]),
         "b200zk_dev_alloc": (i, [vp, sz, C.POINTER(vp)]),
         "b200zk_dev_free": (i, [vp, vp]),
+        "b200zk_host_alloc": (i, [vp, sz, C.POINTER(vp)]),
+        "b200zk_host_free": (i, [vp, vp]),
         "b200zk_ipc_export": (i, [vp, vp, vp]),
         "b200zk_ipc_import": (i, [vp, vp, C.POINTER(vp)]),
         "b200zk_ipc_close": (i, [vp, vp]),
@@ -90,6 +93,7 @@ def load() -> C.CDLL:
         "b200zk_plonk_set_commit_hook": (i, [vp, vp, vp]),
         "b200zk_plonk_pk_poly": (i, [vp, vp, i, vp]),
         "b200zk_plonk_prove": (i, [vp, vp, vp, vp, vp]),
+        "b200zk_plonk_unsatisfied_row": (C.c_longlong, [vp]),
         "b200zk_microbench": (i, [vp, i, C.POINTER(C.c_double)]),
         "b200zk_profile_enable": (i, [vp, i]),
         "b200zk_profile_read": (i, [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), i]),

@@ -94,6 +94,7 @@ const char* b200zk_strerror(int code) {
     case B200ZK_ERR_BAD_ARG: return "bad argument";
     case B200ZK_ERR_OOM: return "out of device memory";
     case B200ZK_ERR_UNSUPPORTED: return "unsupported size";
+    case B200ZK_ERR_UNSATISFIED: return "constraint system not satisfied by the solution";
     default: return "unknown error";
   }
 }
@@ -149,6 +150,20 @@ int b200zk_dev_alloc(b200zk_ctx* ctx, size_t bytes, void** out) {
   B200ZK_TRY(enter(ctx));
   if (!out || !bytes) return B200ZK_ERR_BAD_ARG;
   B200ZK_CUDA(ctx, cudaMalloc(out, bytes));
+  return B200ZK_OK;
+}
+
+int b200zk_host_alloc(b200zk_ctx* ctx, size_t bytes, void** out) {
+  B200ZK_TRY(enter(ctx));
+  if (!out || !bytes) return B200ZK_ERR_BAD_ARG;
+  B200ZK_CUDA(ctx, cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+  return B200ZK_OK;
+}
+
+int b200zk_host_free(b200zk_ctx* ctx, void* p) {
+  B200ZK_TRY(enter(ctx));
+  B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  B200ZK_CUDA(ctx, cudaFreeHost(p));
   return B200ZK_OK;
 }
 

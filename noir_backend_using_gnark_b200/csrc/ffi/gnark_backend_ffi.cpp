@@ -83,6 +83,7 @@ struct Keyed {  // everything that depends on (circuit, number of values) only
   b200zk_plonk_pk* pk = nullptr;
   std::vector<uint8_t> vk_bytes;
   uint64_t n = 0, n_big = 0;
+  Fe4* solution = nullptr;  // page-locked staging for the solution vector (one per key, reused by every prove)
   ~Keyed();
 };
 State& state() {
@@ -90,6 +91,7 @@ State& state() {
   return s;
 }
 Keyed::~Keyed() {
+  if (solution && state().ctx) b200zk_host_free(state().ctx, solution);
   if (pk && state().ctx) b200zk_plonk_pk_free(state().ctx, pk);
 }
 size_t cache_capacity() {
@@ -577,28 +579,17 @@ char* PlonkProveWithPK(GoString acirJSON, GoString encodedValues, GoString encod
   trace("proving key checked");
   // BuildWitnesses (common.go:22-43): publics then secrets = wire order
   const size_t nw = k.plan.solution_src.size();
-  std::vector<Fe4> sol(nw ? nw : 1, Fe4{{0, 0, 0, 0}});
-  for (size_t i = 0; i < nw; i++) sol[i] = values[k.plan.solution_src[i]];
-  // spr.Solve: every wire is an input here, so solving is checking (plonk.Prove fails -> log.Fatal, plonk.go:67-70)
-  {
-    std::atomic<size_t> first_bad(SIZE_MAX);
-    const WirePlan& pl = k.plan;
-    parallel_for(cs.size(), 8192, [&](size_t b, size_t e) {
-      auto M = [](const Fe4& x, const Fe4& y) { return host::mul(HFR, x, y); };
-      auto A = [](const Fe4& x, const Fe4& y) { return host::add(HFR, x, y); };
-      for (size_t g = b; g < e; g++) {
-        const Fe4 &xa = sol[pl.a[g]], &xb = sol[pl.b[g]], &xc = sol[pl.c[g]];
-        Fe4 v = A(A(A(M(cs.ql[g], xa), M(cs.qr[g], xb)), A(M(cs.qo[g], xc), M(M(cs.qm[g], xa), xb))), cs.qk[g]);
-        if (!host::is_zero(v)) {
-          size_t cur = first_bad.load();
-          while (g < cur && !first_bad.compare_exchange_weak(cur, g)) {}
-          return;
-        }
-      }
-    });
-    if (first_bad.load() != SIZE_MAX) fatal("constraint #" + std::to_string(first_bad.load()) + " is not satisfied");
+  if (!k.solution) {
+    void* p = nullptr;
+    check(b200zk_host_alloc(context(), (nw ? nw : 1) * sizeof(Fe4), &p), "b200zk_host_alloc");
+    k.solution = (Fe4*)p;
+    k.solution[0] = Fe4{{0, 0, 0, 0}};
   }
-  trace("witness + constraint check");
+  Fe4* sol = k.solution;
+  parallel_for(nw, (size_t)1 << 16, [&](size_t b, size_t e) {
+    for (size_t i = b; i < e; i++) sol[i] = values[k.plan.solution_src[i]];
+  });
+  trace("solution vector");
   Fe4 blinding[9];
   if (const char* seed = getenv("B200ZK_BLINDING_SEED")) {
     uint64_t st = strtoull(seed, nullptr, 0);
@@ -621,7 +612,12 @@ char* PlonkProveWithPK(GoString acirJSON, GoString encodedValues, GoString encod
     fclose(ur);
   }
   uint8_t blob[832];
-  check(b200zk_plonk_prove(context(), k.pk, sol.data(), blinding, blob), "plonk.Prove");
+  // every wire is an input here, so spr.Solve amounts to checking each constraint: done on the device at the start of
+  // the prover; plonk.Prove's error is fatal in the reference (plonk.go:67-70)
+  const int rc = b200zk_plonk_prove(context(), k.pk, sol, blinding, blob);
+  if (rc == B200ZK_ERR_UNSATISFIED)
+    fatal("constraint #" + std::to_string(b200zk_plonk_unsatisfied_row(k.pk) - (long long)k.plan.nb_public) + " is not satisfied");
+  check(rc, "plonk.Prove");
   trace("plonk.Prove (device)");
   return c_string(hex_encode(serialize_proof(blob)));
 }

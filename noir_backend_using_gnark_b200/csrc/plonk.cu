@@ -68,6 +68,27 @@ __global__ void k_gather_lro(const uint4* __restrict__ sol, const uint32_t* __re
   o[2 * i] = sol[2 * (size_t)c]; o[2 * i + 1] = sol[2 * (size_t)c + 1];
 }
 
+// spr.Solve's acceptance test, row by row: ql*l + qr*r + qm*l*r + qo*o + qk (+ public input on the placeholder rows)
+// must vanish; the smallest failing row lands in *bad_row
+__global__ void k_check_gates(const uint4* __restrict__ ql, const uint4* __restrict__ qr, const uint4* __restrict__ qm,
+                              const uint4* __restrict__ qo, const uint4* __restrict__ lqk, const uint4* __restrict__ l,
+                              const uint4* __restrict__ r, const uint4* __restrict__ o, const uint4* __restrict__ sol,
+                              unsigned nb_public, size_t n, uint32_t* bad_row) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Fr a = fe_load<FrParams>(l + 2 * i), b = fe_load<FrParams>(r + 2 * i), c = fe_load<FrParams>(o + 2 * i);
+  Fr v = fe_load<FrParams>(lqk + 2 * i);
+  if (i < nb_public) v = fe_add(v, fe_load<FrParams>(sol + 2 * i));
+  v = fe_add(v, fe_mul(fe_load<FrParams>(ql + 2 * i), a));
+  v = fe_add(v, fe_mul(fe_load<FrParams>(qr + 2 * i), b));
+  v = fe_add(v, fe_mul(fe_mul(fe_load<FrParams>(qm + 2 * i), a), b));
+  v = fe_add(v, fe_mul(fe_load<FrParams>(qo + 2 * i), c));
+  uint32_t nz = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) nz |= v.l[k];
+  if (nz) atomicMin(bad_row, (uint32_t)i);
+}
+
 __global__ void k_fill(uint4* dst, size_t count, FrArg v) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= count) return;
@@ -449,6 +470,9 @@ struct b200zk_plonk_pk {
   char* arena = nullptr;  // one allocation; all pointers below point into it
   // static (circuit) data
   uint4 *ql, *qr, *qm, *qo, *cqk, *lqk, *s1, *s2, *s3;        // canonical (lqk: Lagrange), n each
+  uint4 *lql, *lqr, *lqm, *lqo;                                // Lagrange selectors, for the per-row constraint check
+  uint32_t* bad_row;                                           // first unsatisfied row of the last prove (device)
+  long long last_bad_row = -1;
   uint4 *e_ql, *e_qr, *e_qm, *e_qo, *e_s1, *e_s2, *e_s3, *e_lone;  // Lagrange-coset bit-reversed, N4 each
   int64_t* perm;
   uint32_t* lro;
@@ -482,7 +506,7 @@ void carve(b200zk_plonk_pk* pk, char* base, size_t* total) {
   const size_t small = (n + 8) * 32, big = N4 * 32;
   uint4** smalls[] = {&pk->ql, &pk->qr, &pk->qm, &pk->qo, &pk->cqk, &pk->lqk, &pk->s1, &pk->s2, &pk->s3,
                       &pk->l, &pk->r, &pk->o, &pk->bl, &pk->br, &pk->bo, &pk->bz, &pk->qk,
-                      &pk->lin, &pk->folded_h, &pk->folded, &pk->quot};
+                      &pk->lin, &pk->folded_h, &pk->folded, &pk->quot, &pk->lql, &pk->lqr, &pk->lqm, &pk->lqo};
   for (auto s : smalls) *s = c.take<uint4>(small);
   uint4** bigs[] = {&pk->e_ql, &pk->e_qr, &pk->e_qm, &pk->e_qo, &pk->e_s1, &pk->e_s2, &pk->e_s3, &pk->e_lone,
                     &pk->el, &pk->er, &pk->eo, &pk->ez, &pk->eqk, &pk->t};
@@ -494,6 +518,7 @@ void carve(b200zk_plonk_pk* pk, char* base, size_t* total) {
   pk->chunks = c.take<uint4>((N4 / 32 + 2048) * 32);
   pk->partials = c.take<uint4>((N4 / (32 * 256) + 64) * 32);
   pk->scal = c.take<uint4>(64 * 32);
+  pk->bad_row = c.take<uint32_t>(256);
   pk->points = c.take<void>(24 * 64);  // 16 result slots + device copy of the 8 vk points
   *total = c.off;
 }
@@ -649,7 +674,9 @@ int b200zk_plonk_setup(b200zk_ctx* ctx, const b200zk_bases* bases, unsigned log2
   PK_CUDA(cudaMemcpyAsync(pk->lqk, qk_l, n * 32, cudaMemcpyHostToDevice, st));
   PK_CUDA(cudaMemcpyAsync(pk->perm, permutation, 3 * n * 8, cudaMemcpyHostToDevice, st));
   PK_CUDA(cudaMemcpyAsync(pk->lro, lro, 3 * n * 4, cudaMemcpyHostToDevice, st));
-  // selectors -> canonical
+  // selectors -> canonical (the Lagrange forms of ql, qr, qm, qo stay for the prover's constraint check)
+  uint4* ldst[4] = {pk->lql, pk->lqr, pk->lqm, pk->lqo};
+  for (int i = 0; i < 4; i++) PK_CUDA(cudaMemcpyAsync(ldst[i], hdst[i], n * 32, cudaMemcpyDeviceToDevice, st));
   for (int i = 0; i < 5; i++) PK_TRY(to_canonical(ctx, hdst[i], log2n));
   // permutation polynomials (needs the domain-n twiddles: built by the transforms above)
   const uint4* tw_n = (const uint4*)ctx->domains[log2n].tw_fwd;
@@ -727,6 +754,8 @@ int b200zk_plonk_setup_r1cs(b200zk_ctx* ctx, const b200zk_bases* bases, unsigned
                             cols[3].data(), cols[4].data(), perm.data(), lro.data(), out);
 }
 
+long long b200zk_plonk_unsatisfied_row(const b200zk_plonk_pk* pk) { return pk ? pk->last_bad_row : -1; }
+
 void b200zk_plonk_pk_free(b200zk_ctx* ctx, b200zk_plonk_pk* pk) {
   if (!pk) return;
   if (ctx) {
@@ -781,6 +810,13 @@ int b200zk_plonk_prove(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solutio
   // P1-P4: L,R,O in Lagrange form, canonical, blinded, committed
   k_gather_lro<<<nblocks(n, 256), 256, 0, st>>>(pk->sol, pk->lro, n, pk->l, pk->r, pk->o);
   B200ZK_LAUNCH_CHECK(ctx, "k_gather_lro");
+  // what spr.Solve would reject (plonk.Prove returns its error before committing to anything)
+  B200ZK_CUDA(ctx, cudaMemsetAsync(pk->bad_row, 0xff, 4, st));
+  k_check_gates<<<nblocks(n, 256), 256, 0, st>>>(pk->lql, pk->lqr, pk->lqm, pk->lqo, pk->lqk, pk->l, pk->r, pk->o, pk->sol,
+                                                 pk->nb_public, n, pk->bad_row);
+  B200ZK_LAUNCH_CHECK(ctx, "k_check_gates");
+  uint32_t bad_row = 0xffffffffu;
+  B200ZK_CUDA(ctx, cudaMemcpyAsync(&bad_row, pk->bad_row, 4, cudaMemcpyDeviceToHost, st));
   uint4* lag[3] = {pk->l, pk->r, pk->o};
   uint4* can[3] = {pk->bl, pk->br, pk->bo};
   for (int k = 0; k < 3; k++) {
@@ -791,7 +827,9 @@ int b200zk_plonk_prove(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solutio
     B200ZK_LAUNCH_CHECK(ctx, "k_blind");
   }
   for (int k = 0; k < 3; k++) B200ZK_TRY(commit(ctx, pk, can[k], n + 2, 8 + k));
-  B200ZK_TRY(fetch_points(ctx, pk, 8, 3, pts));  // pts[0..2] = LRO
+  B200ZK_TRY(fetch_points(ctx, pk, 8, 3, pts));  // pts[0..2] = LRO (the sync also lands bad_row)
+  pk->last_bad_row = bad_row == 0xffffffffu ? -1 : (long long)bad_row;
+  if (pk->last_bad_row >= 0) return B200ZK_ERR_UNSATISFIED;
 
   // P5: gamma, beta
   Transcript fs;

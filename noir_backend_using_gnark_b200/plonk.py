@@ -136,6 +136,14 @@ def build_permutation(lro: np.ndarray) -> np.ndarray:
     return perm
 
 
+class UnsatisfiedConstraint(ValueError):
+    """The solution vector violates constraint #index (what gnark's solver reports from plonk.Prove)."""
+
+    def __init__(self, index: int):
+        super().__init__("constraint #%d is not satisfied" % index)
+        self.index = index
+
+
 @dataclass
 class Proof:
     """plonk.Proof of gnark v0.8.0 (bn254): points as 64-byte G1Affine images, scalars as 32-byte fr images."""
@@ -275,6 +283,9 @@ class ProvingKey:
         assert sol.nbytes == self.nb_wires * 32 and bl.nbytes == 9 * 32
         out = np.zeros(832, dtype=np.uint8)
         rc = self.ctx.lib.b200zk_plonk_prove(self.ctx.handle, self.handle, sol.ctypes.data, bl.ctypes.data, out.ctypes.data)
+        if rc == _lib.ERR_UNSATISFIED:  # plonk.Prove returns spr.Solve's error before committing to anything
+            row = self.ctx.lib.b200zk_plonk_unsatisfied_row(self.handle)
+            raise UnsatisfiedConstraint(row - self.nb_public)
         _lib.check(self.ctx.handle, rc)
         return Proof(out.tobytes())
 

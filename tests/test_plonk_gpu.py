@@ -118,3 +118,25 @@ def test_plonk_api_rejects_bad_arguments(ctx):
     assert lib.b200zk_plonk_prove(ctx.handle, None, buf.ctypes.data, buf.ctypes.data, buf.ctypes.data) == -3
     assert lib.b200zk_plonk_vk(ctx.handle, None, buf.ctypes.data) == -3
     srs.close()
+
+
+def test_unsatisfied_solution_is_refused_like_the_solver(ctx):
+    """plonk.Prove fails in spr.Solve on a violated constraint; the device prover checks every row and names the
+    same (first) constraint as the oracle's solver."""
+    cs_o, x = pl.synthetic_chain_circuit(300, 0xB2000004, 2)
+    srs_d = zk.SRS.NewSRS(600, o.fr_to_mont_bytes([ALPHA]), ctx)
+    pk_d = zkp.ProvingKey.Setup(to_product_cs(cs_o), srs_d, ctx)
+    blind = blinding_bytes(1)
+    good = pk_d.Prove(o.fr_to_mont_bytes(x), blind)
+    for wire in (len(x) - 1, 150, 5):
+        bad = list(x)
+        bad[wire] = (bad[wire] + 1) % o.R_MOD
+        with pytest.raises(ValueError) as want:
+            pl.solve(cs_o, bad)
+        with pytest.raises(zkp.UnsatisfiedConstraint) as got:
+            pk_d.Prove(o.fr_to_mont_bytes(bad), blind)
+        assert str(got.value) in str(want.value) or "#%d" % got.value.index in str(want.value), (str(got.value), str(want.value))
+    # a wrong PUBLIC input is not a constraint violation (the placeholder rows take whatever is supplied)
+    assert pk_d.Prove(o.fr_to_mont_bytes(x), blind).blob == good.blob      # the key still proves after refusals
+    pk_d.close()
+    srs_d.close()
