@@ -138,6 +138,9 @@ int b200zk_g1_sum_dev(b200zk_ctx* ctx, const void* partials_dev, size_t count, v
 /* tests / tuning: 0 / 1 = one-level scatter (default: all of a point's returning atomics in flight at once),
  * 2 = two-level scatter (partition by high bucket bits, then shared-memory cursors; slower on B200, kept for comparison) */
 int b200zk_msm_set_flat_scatter(b200zk_ctx* ctx, int on);
+/* b200zk_msm_g1 (host scalars) splits large inputs by point range so that the host-to-device copy of one chunk runs
+ * under the MSM of the previous one; 0 = choose from n (2 chunks from 2^23 points: measured best, scripts/e2e_chunks.py), 1 = never split, up to 8 */
+int b200zk_msm_set_host_chunks(b200zk_ctx* ctx, int chunks);
 /* force the Pippenger window size (0 = choose from n); for tests and tuning */
 int b200zk_msm_set_window(b200zk_ctx* ctx, int c);
 /* measurement: the number of windows (= bucket additions per point) an MSM of n points of these bases will use

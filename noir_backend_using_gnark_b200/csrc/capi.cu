@@ -58,6 +58,12 @@ int b200zk_init(int device, b200zk_ctx** out) {
     delete ctx;
     return B200ZK_ERR_CUDA;
   }
+  for (auto& ev : ctx->ev_chunk)
+    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      delete ctx;
+      return B200ZK_ERR_CUDA;
+    }
   *out = ctx;
   return B200ZK_OK;
 }
@@ -83,6 +89,8 @@ void b200zk_destroy(b200zk_ctx* ctx) {
   if (ctx->side) cudaStreamDestroy(ctx->side);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  for (auto ev : ctx->ev_chunk)
+    if (ev) cudaEventDestroy(ev);
   delete ctx;
 }
 
@@ -296,13 +304,48 @@ int b200zk_msm_g1(b200zk_ctx* ctx, const b200zk_bases* bases, const void* scalar
                   void* out_affine_host) {
   B200ZK_TRY(enter(ctx));
   if (!bases || !out_affine_host || (n && !scalars_host) || n > bases->n) return B200ZK_ERR_BAD_ARG;
-  const size_t bytes = n * 32 + 64;
+  const size_t head = 64 + 8 * 128;  // result + up to 8 partial sums
+  const size_t bytes = n * 32 + head;
   B200ZK_TRY(ensure(ctx, ctx->stage, bytes));
   char* stage = (char*)ctx->stage.p;
-  if (n) B200ZK_CUDA(ctx, cudaMemcpyAsync(stage + 64, scalars_host, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-  B200ZK_TRY(msm_run(ctx, bases, 0, stage + 64, n, stage, 0));
+  char* sc = stage + head;
+  // Large inputs are split by point range so that the PCIe copy of chunk i+1 runs under the MSM of chunk i
+  // (the sum of the partial MSMs is the MSM: the canonical affine result does not depend on the split).
+  unsigned chunks = ctx->msm_host_chunks > 0 ? (unsigned)ctx->msm_host_chunks : (n >= ((size_t)1 << 23) ? 2u : 1u);
+  if (chunks > 8) chunks = 8;
+  if (n < 4096 * (size_t)chunks) chunks = 1;
+  if (chunks == 1) {
+    if (n) B200ZK_CUDA(ctx, cudaMemcpyAsync(sc, scalars_host, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    B200ZK_TRY(msm_run(ctx, bases, 0, sc, n, stage, 0));
+  } else {
+    const size_t per = (n + chunks - 1) / chunks;
+    // the copy stream must not overtake earlier work on the compute stream that still reads the staging buffer
+    B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    B200ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+    auto copy_chunk = [&](unsigned i) -> int {
+      const size_t first = (size_t)i * per, cnt = first + per <= n ? per : n - first;
+      B200ZK_CUDA(ctx, cudaMemcpyAsync(sc + first * 32, (const char*)scalars_host + first * 32, cnt * 32, cudaMemcpyHostToDevice,
+                                       ctx->side));
+      B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev_chunk[i], ctx->side));
+      return B200ZK_OK;
+    };
+    B200ZK_TRY(copy_chunk(0));
+    for (unsigned i = 0; i < chunks; i++) {
+      if (i + 1 < chunks) B200ZK_TRY(copy_chunk(i + 1));
+      const size_t first = (size_t)i * per, cnt = first + per <= n ? per : n - first;
+      B200ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[i], 0));
+      B200ZK_TRY(msm_run(ctx, bases, first, sc + first * 32, cnt, stage + 64 + 128 * i, 1));
+    }
+    B200ZK_TRY(g1_sum_run(ctx, stage + 64, chunks, stage));
+  }
   B200ZK_CUDA(ctx, cudaMemcpyAsync(out_affine_host, stage, 64, cudaMemcpyDeviceToHost, ctx->stream));
   B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200ZK_OK;
+}
+
+int b200zk_msm_set_host_chunks(b200zk_ctx* ctx, int chunks) {
+  if (!ctx || chunks < 0 || chunks > 8) return B200ZK_ERR_BAD_ARG;
+  ctx->msm_host_chunks = chunks;
   return B200ZK_OK;
 }
 

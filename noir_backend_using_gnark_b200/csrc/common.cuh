@@ -56,6 +56,8 @@ struct b200zk_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t side = nullptr;  // latency-bound single-warp work that overlaps the big kernels (prover digests)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_chunk[8] = {};  // host-scalar MSM: chunk i of the scalars has landed (copy stream -> compute stream)
+  int msm_host_chunks = 0;       // 0 = choose from n; 1 = never split (tests / tuning)
   uint64_t launches = 0;
   char cuda_err[256] = {0};
   int forced_window = 0;

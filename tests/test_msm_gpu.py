@@ -282,3 +282,31 @@ def test_flat_and_two_level_scatter_agree(ctx):
             assert zk.MultiExp(srs, sc) == want, (table, flat)
     lib.b200zk_msm_set_flat_scatter(ctx.handle, 0)
     srs.close()
+
+
+@pytest.mark.parametrize("chunks", [2, 3, 4, 8])
+def test_host_scalar_msm_split_for_copy_overlap(ctx, chunks):
+    """b200zk_msm_g1 splits host scalars by point range (copy of chunk i+1 under the MSM of chunk i): the result must
+    not depend on the split — classic windows, window table, ragged last chunk, pageable and pinned host buffers."""
+    import torch
+
+    lib = zk.load()
+    n = (1 << 16) + 777
+    pts = structured(n)
+    sc = cref.random_fr(n, 0xB2000001 + 5)
+    want = cref.msm(pts, sc, n, nthreads=cref.ncores())
+    srs = zk.SRS(pts, ctx)
+    try:
+        for table in (False, True):
+            if table:
+                srs.precompute()
+            lib.b200zk_msm_set_host_chunks(ctx.handle, 1)
+            assert zk.MultiExp(srs, sc) == want
+            lib.b200zk_msm_set_host_chunks(ctx.handle, chunks)
+            assert zk.MultiExp(srs, sc) == want, (table, chunks)
+            pinned = torch.from_numpy(sc.copy()).pin_memory()
+            assert zk.MultiExp(srs, pinned.numpy()) == want
+            assert zk.MultiExp(srs, sc[: 5000 * 32], n=5000) == cref.msm(pts, sc, 5000, nthreads=2)   # too small: not split
+    finally:
+        lib.b200zk_msm_set_host_chunks(ctx.handle, 0)
+        srs.close()
