@@ -88,3 +88,36 @@ def test_malformed_payloads_are_fatal_like_log_fatal(proved, field, value, needl
     step[field] = value
     rc, res, err = run_child([step], home)
     assert rc == 1 and needle in err, (rc, err)          # main.go:29,49,64,71: log.Fatal -> exit status 1
+
+
+def test_mutated_payloads_never_crash(proved):
+    """Byte-level mutations of every PlonkVerifyWithVK payload: the call must end as the reference would — a 0/1 answer
+    or log.Fatal's exit status 1 — never by a signal."""
+    import random
+
+    home, cases = proved
+    js, vals, vk, proof = cases[0]
+    base = {"op": "raw_verify", "acir": js, "values": ff.felts_hex(vals), "vk": vk.hex(), "proof": proof.hex()}
+    rng = random.Random(0xB200F)
+    outcomes = set()
+    for trial in range(14):
+        step = dict(base)
+        field = ["acir", "values", "vk", "proof"][trial % 4]
+        s = step[field]
+        kind = rng.randrange(4)
+        pos = rng.randrange(len(s))
+        if kind == 0:
+            s = s[:pos]                                              # truncation
+        elif kind == 1:
+            s = s[:pos] + rng.choice("0123456789abcdef{}[]\",:x") + s[pos + 1:]   # one character replaced
+        elif kind == 2:
+            s = s[:pos] + s[pos:pos + 7] * 3 + s[pos:]               # a run duplicated
+        else:
+            s = s + s[:pos]                                          # trailing garbage
+        step[field] = s
+        rc, res, err = run_child([step], home)
+        assert rc in (0, 1), (field, kind, rc, err[-200:])
+        if rc == 0:
+            assert res in ([0], [1])
+        outcomes.add((rc, tuple(res) if res else None))
+    assert len(outcomes) >= 2
