@@ -195,6 +195,15 @@ int b200zk_plonk_pk_poly(b200zk_ctx* ctx, const b200zk_plonk_pk* pk, int which, 
 int b200zk_plonk_prove(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solution_host, const void* blinding_host,
                        void* proof_out);
 long long b200zk_plonk_unsatisfied_row(const b200zk_plonk_pk* pk);
+/* The same prover fed with what PlonkProveWithPK receives (/root/reference/gnark_backend_ffi/main.go:24-37): the hex text of
+ * the value vector, 64 characters per element (32 bytes big-endian, regular form), WITHOUT the 8-character count prefix.
+ * DeserializeFelts (fr.SetBytes: reduce, Montgomery form) and BuildWitnesses (values -> publics then secrets) run on the
+ * device: set_solution_map stores, once per key, which value feeds which wire (wire k <- values[src[k]], nb_wires
+ * entries, every entry < nb_values); prove_hex uploads the text, decodes, gathers and proves.  A non-hex character
+ * returns B200ZK_ERR_BAD_ARG (hex.DecodeString's error), before anything is committed. */
+int b200zk_plonk_set_solution_map(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const uint32_t* src_host, size_t nb_values);
+int b200zk_plonk_prove_hex(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const char* values_hex_host, size_t nb_values,
+                           const void* blinding_host, void* proof_out);
 
 /* ---- measurement ----------------------------------------------------------------------------------------
  * Integer-pipe microbenchmarks used as roofline denominators (synchronous).  which = 0: IMAD.WIDE.U32 multiply-

@@ -84,6 +84,7 @@ struct Keyed {  // everything that depends on (circuit, number of values) only
   std::vector<uint8_t> vk_bytes;
   uint64_t n = 0, n_big = 0;
   Fe4* solution = nullptr;  // page-locked staging for the solution vector (one per key, reused by every prove)
+  bool map_on_device = false;  // b200zk_plonk_set_solution_map done
   ~Keyed();
 };
 State& state() {
@@ -555,42 +556,8 @@ struct PlonkPreprocess_return PlonkPreprocess(GoString acirJSON, GoString encode
   return r;
 }
 
-char* PlonkProveWithPK(GoString acirJSON, GoString encodedValues, GoString encodedProvingKey) {  // main.go:24-37
-  Trace trace("PlonkProveWithPK");
-  std::vector<Fe4> values = felts_from_hex(span_of(encodedValues));
-  trace("values decoded");
-  State::Entry& entry = circuit_entry(span_of(acirJSON));
-  const Circuit& cs = *entry.circuit;
-  trace("circuit read / found");
-  Keyed& k = keyed(entry, values.size());
-  ensure_key(cs, k);
-  trace("key resident");
-  // DeserializeProvingKey (helpers.go:49-60): the polynomials of the key are already resident on the device (derived
-  // from the same circuit and SRS; the reference itself re-derives the key's coset forms on every call), so the
-  // payload is checked, not re-read: its length must be that of ProvingKey.WriteTo for this circuit and the
-  // verifying key it starts with must be the one derived here.
-  {
-    Span pk = span_of(encodedProvingKey);
-    if (pk.n % 2) fatal("encoding/hex: odd length hex string");
-    if (pk.n != 2 * pk_stream_bytes(k)) fatal(pk.n < 2 * pk_stream_bytes(k) ? "unexpected EOF reading the proving key" : "proving key does not belong to this circuit (size mismatch)");
-    std::vector<uint8_t> head = hex_decode(Span{pk.p, 2 * k.vk_bytes.size()});
-    if (head != k.vk_bytes) fatal("proving key does not belong to this circuit and SRS");
-  }
-  trace("proving key checked");
-  // BuildWitnesses (common.go:22-43): publics then secrets = wire order
-  const size_t nw = k.plan.solution_src.size();
-  if (!k.solution) {
-    void* p = nullptr;
-    check(b200zk_host_alloc(context(), (nw ? nw : 1) * sizeof(Fe4), &p), "b200zk_host_alloc");
-    k.solution = (Fe4*)p;
-    k.solution[0] = Fe4{{0, 0, 0, 0}};
-  }
-  Fe4* sol = k.solution;
-  parallel_for(nw, (size_t)1 << 16, [&](size_t b, size_t e) {
-    for (size_t i = b; i < e; i++) sol[i] = values[k.plan.solution_src[i]];
-  });
-  trace("solution vector");
-  Fe4 blinding[9];
+// the 9 blinding scalars of plonk.Prove: fr.SetRandom draws (their limbs are the Montgomery form)
+static void draw_blinding(Fe4 blinding[9]) {
   if (const char* seed = getenv("B200ZK_BLINDING_SEED")) {
     uint64_t st = strtoull(seed, nullptr, 0);
     for (int i = 0; i < 9;) {
@@ -605,16 +572,84 @@ char* PlonkProveWithPK(GoString acirJSON, GoString encodedValues, GoString encod
       v.l[3] &= 0x3fffffffffffffffULL;
       if (!host::geq(v.l, HFR.m)) blinding[i++] = v;
     }
-  } else {
-    FILE* ur = fopen("/dev/urandom", "rb");
-    if (!ur) fatal("cannot open /dev/urandom");
-    for (int i = 0; i < 9; i++) blinding[i] = random_fr(ur);  // limbs are the Montgomery form (fr.SetRandom)
-    fclose(ur);
+    return;
   }
+  FILE* ur = fopen("/dev/urandom", "rb");
+  if (!ur) fatal("cannot open /dev/urandom");
+  for (int i = 0; i < 9; i++) blinding[i] = random_fr(ur);
+  fclose(ur);
+}
+
+// hex(u32-BE count || 32-byte elements) with a complete body: the count, else false (short / empty payloads take the
+// host path, which reproduces the reference's ignored UnmarshalBinary error)
+static bool felts_count(Span h, size_t* count) {
+  if (h.n % 2 || h.n < 8) return false;
+  uint8_t head[4];
+  if (!hex_decode_into(Span{h.p, 8}, head)) return false;
+  const size_t n = ((size_t)head[0] << 24) | ((size_t)head[1] << 16) | ((size_t)head[2] << 8) | head[3];
+  if (n == 0 || (h.n - 8) / 64 < n) return false;
+  *count = n;
+  return true;
+}
+
+char* PlonkProveWithPK(GoString acirJSON, GoString encodedValues, GoString encodedProvingKey) {  // main.go:24-37
+  Trace trace("PlonkProveWithPK");
+  const Span payload = span_of(encodedValues);
+  size_t nvalues = 0;
+  const bool on_device = felts_count(payload, &nvalues);  // DeserializeFelts + BuildWitnesses run on the GPU
+  std::vector<Fe4> values;
+  if (!on_device) {
+    values = felts_from_hex(payload);
+    nvalues = values.size();
+  } else if (payload.n > 8 + 64 * nvalues) {  // bytes after the vector are ignored by UnmarshalBinary but must be hex
+    std::vector<uint8_t> tmp((payload.n - 8 - 64 * nvalues) / 2);
+    if (!hex_decode_into(Span{payload.p + 8 + 64 * nvalues, payload.n - 8 - 64 * nvalues}, tmp.data()))
+      fatal("encoding/hex: invalid byte");
+  }
+  trace("values header / host decode");
+  State::Entry& entry = circuit_entry(span_of(acirJSON));
+  const Circuit& cs = *entry.circuit;
+  trace("circuit read / found");
+  Keyed& k = keyed(entry, nvalues);
+  ensure_key(cs, k);
+  trace("key resident");
+  // DeserializeProvingKey (helpers.go:49-60): the polynomials of the key are already resident on the device (derived
+  // from the same circuit and SRS; the reference itself re-derives the key's coset forms on every call), so the
+  // payload is checked, not re-read: its length must be that of ProvingKey.WriteTo for this circuit and the
+  // verifying key it starts with must be the one derived here.
+  {
+    Span pk = span_of(encodedProvingKey);
+    if (pk.n % 2) fatal("encoding/hex: odd length hex string");
+    if (pk.n != 2 * pk_stream_bytes(k)) fatal(pk.n < 2 * pk_stream_bytes(k) ? "unexpected EOF reading the proving key" : "proving key does not belong to this circuit (size mismatch)");
+    std::vector<uint8_t> head = hex_decode(Span{pk.p, 2 * k.vk_bytes.size()});
+    if (head != k.vk_bytes) fatal("proving key does not belong to this circuit and SRS");
+  }
+  trace("proving key checked");
+  Fe4 blinding[9];
+  draw_blinding(blinding);
   uint8_t blob[832];
+  int rc;
+  const size_t nw = k.plan.solution_src.size();
+  if (on_device && nw) {
+    if (!k.map_on_device) {
+      check(b200zk_plonk_set_solution_map(context(), k.pk, k.plan.solution_src.data(), nvalues), "b200zk_plonk_set_solution_map");
+      k.map_on_device = true;
+    }
+    rc = b200zk_plonk_prove_hex(context(), k.pk, payload.p + 8, nvalues, blinding, blob);
+    if (rc == B200ZK_ERR_BAD_ARG) fatal("encoding/hex: invalid byte");
+  } else {
+    // BuildWitnesses (common.go:22-43) on the host: publics then secrets = wire order
+    if (!k.solution) {
+      void* p = nullptr;
+      check(b200zk_host_alloc(context(), (nw ? nw : 1) * sizeof(Fe4), &p), "b200zk_host_alloc");
+      k.solution = (Fe4*)p;
+      k.solution[0] = Fe4{{0, 0, 0, 0}};
+    }
+    for (size_t i = 0; i < nw; i++) k.solution[i] = values[k.plan.solution_src[i]];
+    rc = b200zk_plonk_prove(context(), k.pk, k.solution, blinding, blob);
+  }
   // every wire is an input here, so spr.Solve amounts to checking each constraint: done on the device at the start of
   // the prover; plonk.Prove's error is fatal in the reference (plonk.go:67-70)
-  const int rc = b200zk_plonk_prove(context(), k.pk, sol, blinding, blob);
   if (rc == B200ZK_ERR_UNSATISFIED)
     fatal("constraint #" + std::to_string(b200zk_plonk_unsatisfied_row(k.pk) - (long long)k.plan.nb_public) + " is not satisfied");
   check(rc, "plonk.Prove");

@@ -89,6 +89,47 @@ __global__ void k_check_gates(const uint4* __restrict__ ql, const uint4* __restr
   if (nz) atomicMin(bad_row, (uint32_t)i);
 }
 
+// DeserializeFelts on the device: 64 hex characters per element (32 bytes big-endian, regular form) ->
+// fr.Element.SetBytes (reduce mod r, Montgomery form).  A non-hex character raises *bad.
+__global__ void k_hex_to_fr(const uint4* __restrict__ hex, size_t n, uint4* out, unsigned* bad) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr v;
+  unsigned invalid = 0;
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const uint4 h = hex[4 * i + q];
+    const uint32_t w[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      uint32_t half = 0;  // 4 characters -> 16 bits, first character most significant
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const uint32_t c = (w[j] >> (8 * k)) & 0xffu;
+        const uint32_t dig = c - '0', let = (c | 0x20u) - 'a';
+        invalid |= (dig >= 10u) & (let >= 6u);
+        half = (half << 4) | (dig < 10u ? dig : let + 10u);
+      }
+      const int word = 4 * q + j;  // 0..15, most significant first
+      if (word & 1) v.l[7 - word / 2] |= half;
+      else v.l[7 - word / 2] = half << 16;
+    }
+  }
+  if (invalid) atomicOr(bad, 1u);
+#pragma unroll 1
+  for (int k = 0; k < 5; k++) final_sub<FrParams>(v.l);  // 2^256 < 6r: five conditional subtractions reduce any input
+  fe_store(out + 2 * i, fe_to_mont(v));
+}
+
+// BuildWitnesses on the device: wire k <- values[src[k]]
+__global__ void k_gather_fr(const uint4* __restrict__ values, const uint32_t* __restrict__ src, size_t count, uint4* sol) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const size_t s = src[i];
+  sol[2 * i] = values[2 * s];
+  sol[2 * i + 1] = values[2 * s + 1];
+}
+
 __global__ void k_fill(uint4* dst, size_t count, FrArg v) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= count) return;
@@ -473,6 +514,8 @@ struct b200zk_plonk_pk {
   uint4 *lql, *lqr, *lqm, *lqo;                                // Lagrange selectors, for the per-row constraint check
   uint32_t* bad_row;                                           // first unsatisfied row of the last prove (device)
   long long last_bad_row = -1;
+  uint32_t* sol_src = nullptr;   // optional (b200zk_plonk_set_solution_map): wire k <- values[sol_src[k]], own allocation
+  size_t map_values = 0;
   uint4 *e_ql, *e_qr, *e_qm, *e_qo, *e_s1, *e_s2, *e_s3, *e_lone;  // Lagrange-coset bit-reversed, N4 each
   int64_t* perm;
   uint32_t* lro;
@@ -763,6 +806,7 @@ void b200zk_plonk_pk_free(b200zk_ctx* ctx, b200zk_plonk_pk* pk) {
     cudaStreamSynchronize(ctx->stream);
   }
   if (pk->arena) cudaFree(pk->arena);
+  if (pk->sol_src) cudaFree(pk->sol_src);
   delete pk;
 }
 
@@ -789,10 +833,12 @@ int b200zk_plonk_pk_poly(b200zk_ctx* ctx, const b200zk_plonk_pk* pk, int which, 
   return B200ZK_OK;
 }
 
-int b200zk_plonk_prove(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solution_host, const void* blinding_host,
-                       void* proof_out) {
-  if (!ctx || !pk || !solution_host || !blinding_host || !proof_out) return B200ZK_ERR_BAD_ARG;
-  B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+}  // extern "C"
+
+// The prover proper.  solution_host != null: the solution vector is copied up first; null: pk->sol has already been
+// filled on the device by work enqueued on the context stream (b200zk_plonk_prove_hex).
+static int prove_impl(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solution_host, const void* blinding_host,
+                      void* proof_out) {
   cudaStream_t st = ctx->stream;
   const unsigned log2n = pk->log2n, logb = pk->log_big;
   const size_t n = (size_t)1 << log2n, N4 = (size_t)1 << logb;
@@ -804,8 +850,14 @@ int b200zk_plonk_prove(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solutio
   // the kernels below read the twiddle tables of both domains directly (identity polynomial, permutation support)
   B200ZK_TRY(ntt_prepare(ctx, log2n));
   B200ZK_TRY(ntt_prepare(ctx, logb));
-  B200ZK_CUDA(ctx, cudaMemcpyAsync(pk->sol, solution_host, (size_t)pk->nb_wires * 32, cudaMemcpyHostToDevice, st));
+  if (solution_host)
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(pk->sol, solution_host, (size_t)pk->nb_wires * 32, cudaMemcpyHostToDevice, st));
   B200ZK_CUDA(ctx, cudaMemcpyAsync(pk->blinding, blinding_host, 9 * 32, cudaMemcpyHostToDevice, st));
+  std::vector<Fe4> pub(pk->nb_public);  // public inputs, bound into the transcript
+  if (pk->nb_public) {
+    if (solution_host) memcpy(pub.data(), solution_host, (size_t)pk->nb_public * 32);
+    else B200ZK_CUDA(ctx, cudaMemcpyAsync(pub.data(), pk->sol, (size_t)pk->nb_public * 32, cudaMemcpyDeviceToHost, st));
+  }
 
   // P1-P4: L,R,O in Lagrange form, canonical, blinded, committed
   k_gather_lro<<<nblocks(n, 256), 256, 0, st>>>(pk->sol, pk->lro, n, pk->l, pk->r, pk->o);
@@ -835,11 +887,7 @@ int b200zk_plonk_prove(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solutio
   Transcript fs;
   fs.begin("gamma");
   for (int i = 0; i < 8; i++) fs.bind_point(pk->vk_points + 64 * i);
-  {
-    std::vector<Fe4> pub(pk->nb_public);
-    if (pk->nb_public) memcpy(pub.data(), solution_host, (size_t)pk->nb_public * 32);
-    for (auto& v : pub) fs.bind_fr(v);
-  }
+  for (auto& v : pub) fs.bind_fr(v);  // (landed with the synchronisation of the L,R,O commitments above)
   for (int i = 0; i < 3; i++) fs.bind_point(pts + 64 * i);
   const Fe4 gamma = fs.finish();
   fs.begin("beta");
@@ -1069,6 +1117,52 @@ int b200zk_plonk_prove(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solutio
   memcpy(outp + 9 * 64, claimed, 7 * 32);
   memcpy(outp + 9 * 64 + 7 * 32, &zu, 32);
   return B200ZK_OK;
+}
+
+extern "C" {
+
+int b200zk_plonk_prove(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solution_host, const void* blinding_host,
+                       void* proof_out) {
+  if (!ctx || !pk || !solution_host || !blinding_host || !proof_out) return B200ZK_ERR_BAD_ARG;
+  B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+  return prove_impl(ctx, pk, solution_host, blinding_host, proof_out);
+}
+
+int b200zk_plonk_set_solution_map(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const uint32_t* src_host, size_t nb_values) {
+  if (!ctx || !pk || !src_host || nb_values == 0) return B200ZK_ERR_BAD_ARG;
+  B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+  for (unsigned i = 0; i < pk->nb_wires; i++)
+    if (src_host[i] >= nb_values) return B200ZK_ERR_BAD_ARG;
+  if (!pk->sol_src) B200ZK_CUDA(ctx, cudaMalloc((void**)&pk->sol_src, (size_t)pk->nb_wires * 4));
+  B200ZK_CUDA(ctx, cudaMemcpyAsync(pk->sol_src, src_host, (size_t)pk->nb_wires * 4, cudaMemcpyHostToDevice, ctx->stream));
+  B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  pk->map_values = nb_values;
+  return B200ZK_OK;
+}
+
+int b200zk_plonk_prove_hex(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const char* values_hex_host, size_t nb_values,
+                           const void* blinding_host, void* proof_out) {
+  if (!ctx || !pk || !values_hex_host || !blinding_host || !proof_out) return B200ZK_ERR_BAD_ARG;
+  if (!pk->sol_src || nb_values != pk->map_values) return B200ZK_ERR_BAD_ARG;
+  B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  // staging: [flag 256 B | hex text 64 B per value | decoded values 32 B each]
+  B200ZK_TRY(ensure(ctx, ctx->stage, 256 + nb_values * 96));
+  char* base = (char*)ctx->stage.p;
+  unsigned* bad = (unsigned*)base;
+  uint4* hex = (uint4*)(base + 256);
+  uint4* vals = (uint4*)(base + 256 + nb_values * 64);
+  B200ZK_CUDA(ctx, cudaMemsetAsync(bad, 0, 4, st));
+  B200ZK_CUDA(ctx, cudaMemcpyAsync(hex, values_hex_host, nb_values * 64, cudaMemcpyHostToDevice, st));
+  k_hex_to_fr<<<nblocks(nb_values, 128), 128, 0, st>>>(hex, nb_values, vals, bad);
+  B200ZK_LAUNCH_CHECK(ctx, "k_hex_to_fr");
+  k_gather_fr<<<nblocks(pk->nb_wires, 256), 256, 0, st>>>(vals, pk->sol_src, pk->nb_wires, pk->sol);
+  B200ZK_LAUNCH_CHECK(ctx, "k_gather_fr");
+  unsigned bad_host = 0;
+  B200ZK_CUDA(ctx, cudaMemcpyAsync(&bad_host, bad, 4, cudaMemcpyDeviceToHost, st));
+  B200ZK_CUDA(ctx, cudaStreamSynchronize(st));
+  if (bad_host) return B200ZK_ERR_BAD_ARG;  // encoding/hex: invalid byte
+  return prove_impl(ctx, pk, nullptr, blinding_host, proof_out);
 }
 
 }  // extern "C"

@@ -289,6 +289,25 @@ class ProvingKey:
         _lib.check(self.ctx.handle, rc)
         return Proof(out.tobytes())
 
+    def SetSolutionMap(self, src, nb_values: int) -> None:
+        """BuildWitnesses as a gather: wire k <- values[src[k]] (once per key, for ProveHex)."""
+        src = np.ascontiguousarray(np.asarray(src, dtype=np.uint32))
+        assert src.size == self.nb_wires
+        rc = self.ctx.lib.b200zk_plonk_set_solution_map(self.ctx.handle, self.handle, src.ctypes.data, int(nb_values))
+        _lib.check(self.ctx.handle, rc)
+
+    def ProveHex(self, values_hex: bytes, nb_values: int, blinding) -> Proof:
+        """plonk.Prove fed with the hex text PlonkProveWithPK receives (64 characters per value, no count prefix):
+        decoding, Montgomery conversion and the witness gather run on the device."""
+        assert len(values_hex) == 64 * nb_values
+        bl = np.ascontiguousarray(np.frombuffer(bytes(blinding), dtype=np.uint8) if not isinstance(blinding, np.ndarray) else blinding)
+        out = np.zeros(832, dtype=np.uint8)
+        rc = self.ctx.lib.b200zk_plonk_prove_hex(self.ctx.handle, self.handle, values_hex, nb_values, bl.ctypes.data, out.ctypes.data)
+        if rc == _lib.ERR_UNSATISFIED:
+            raise UnsatisfiedConstraint(self.ctx.lib.b200zk_plonk_unsatisfied_row(self.handle) - self.nb_public)
+        _lib.check(self.ctx.handle, rc)
+        return Proof(out.tobytes())
+
     def close(self) -> None:
         if self.handle and self.ctx.handle:
             self.ctx.lib.b200zk_plonk_pk_free(self.ctx.handle, self.handle)

@@ -30,6 +30,11 @@ def main() -> None:
             G = ffi.GoString.of
             out.append(int(lib.PlonkVerifyWithVK(G(step["acir"].encode()), G(step["proof"].encode()), G(step["values"].encode()),
                                                  G(step["vk"].encode()))))
+        elif op == "raw_prove":  # encoded payloads passed through untouched
+            pk = step["pk"]
+            if pk.startswith("@"):
+                pk = out[int(pk[1:].split(".")[0])]["pk"]
+            out.append(ffi.prove_with_pk_encoded(step["acir"].encode(), step["values"].encode(), pk.encode()))
         elif op == "raw_preprocess":
             lib = ffi.load_ffi()
             kp = lib.PlonkPreprocess(ffi.GoString.of(step["acir"].encode()), ffi.GoString.of(step["values"].encode()))

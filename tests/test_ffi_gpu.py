@@ -142,3 +142,32 @@ def test_key_too_large_for_the_srs_is_fatal(home):
     js = '{"current_witness_index":1,"opcodes":[%s],"public_inputs":[]}' % ops
     rc, res, err = run_child([{"op": "preprocess", "acir": js}], home)
     assert rc == 1 and "SRS" in err, (rc, err)
+
+
+def test_value_payload_edge_cases_on_the_device_decoder(home):
+    """PlonkProveWithPK decodes the hex felts on the device: upper-case digits, values >= r (SetBytes reduces), bytes
+    after the vector, an invalid character inside the vector (fatal like hex.DecodeString), a short vector
+    (UnmarshalBinary's ignored error -> no values -> the constraints cannot hold)."""
+    js, vals = FIXTURES[1]
+    vals = [v % o.R_MOD for v in vals]
+    srs = pl.SRS(128, 0xB2000005)
+    cs, pub, sec = pl.build_sparse_r1cs(pl.decode_acir(js), vals)
+    pk = pl.setup(cs, srs)
+    want = pl.prove(cs, pk, srs, pub + sec, pl.BlindingStream(SEED)).to_bytes().hex()
+    env = {"B200ZK_BLINDING_SEED": str(SEED)}
+    plain = ff.felts_hex(vals)
+    unreduced = "%08x" % len(vals) + "".join("%064x" % (v + o.R_MOD) for v in vals)      # < 2^256, same residues
+    steps = [{"op": "preprocess", "acir": js},
+             {"op": "raw_prove", "acir": js, "values": plain.upper(), "pk": "@0.pk"},
+             {"op": "raw_prove", "acir": js, "values": unreduced, "pk": "@0.pk"},
+             {"op": "raw_prove", "acir": js, "values": plain + "00ff", "pk": "@0.pk"}]
+    rc, res, err = run_child(steps, home, env)
+    assert rc == 0, err
+    assert res[1] == want and res[2] == want and res[3] == want
+    bad = plain[:100] + "g" + plain[101:]
+    rc, res, err = run_child(steps[:1] + [{"op": "raw_prove", "acir": js, "values": bad, "pk": "@0.pk"}], home, env)
+    assert rc == 1 and "hex" in err, (rc, err)
+    rc, res, err = run_child(steps[:1] + [{"op": "raw_prove", "acir": js, "values": plain + "zz", "pk": "@0.pk"}], home, env)
+    assert rc == 1 and "hex" in err, (rc, err)
+    rc, res, err = run_child(steps[:1] + [{"op": "raw_prove", "acir": js, "values": plain[:-64], "pk": "@0.pk"}], home, env)
+    assert rc == 1, (rc, err)      # no values: different key size / unsatisfied system, fatal either way

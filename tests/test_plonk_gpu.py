@@ -140,3 +140,43 @@ def test_unsatisfied_solution_is_refused_like_the_solver(ctx):
     assert pk_d.Prove(o.fr_to_mont_bytes(x), blind).blob == good.blob      # the key still proves after refusals
     pk_d.close()
     srs_d.close()
+
+
+def test_prove_from_hex_text_matches_prove(ctx):
+    """b200zk_plonk_prove_hex (DeserializeFelts + BuildWitnesses on the device) == b200zk_plonk_prove on the decoded,
+    gathered solution: permuted value order, unreduced and upper-case encodings, rejection of a non-hex character."""
+    cs_o, x = pl.synthetic_chain_circuit(500, 0xB2000004, 2)
+    nw = len(x)
+    srs_d = zk.SRS.NewSRS(1100, o.fr_to_mont_bytes([ALPHA]), ctx)
+    pk_d = zkp.ProvingKey.Setup(to_product_cs(cs_o), srs_d, ctx)
+    blind = blinding_bytes(3)
+    want = pk_d.Prove(o.fr_to_mont_bytes(x), blind).blob
+    rng = np.random.default_rng(5)
+    order = rng.permutation(nw + 3)                      # values arrive in another order, with 3 unused extras
+    values = [0] * (nw + 3)
+    src = np.zeros(nw, dtype=np.uint32)
+    for wire in range(nw):
+        values[order[wire]] = x[wire]
+        src[wire] = order[wire]
+    for k in range(nw, nw + 3):
+        values[order[k]] = 12345 + k
+    pk_d.SetSolutionMap(src, nw + 3)
+    text = "".join("%064x" % v for v in values)
+    assert pk_d.ProveHex(text.encode(), nw + 3, blind).blob == want
+    assert pk_d.ProveHex(text.upper().encode(), nw + 3, blind).blob == want
+    for k in range(1, 5):
+        big = "".join("%064x" % (v + o.R_MOD * k) for v in values)                     # still < 2^256
+        assert pk_d.ProveHex(big.encode(), nw + 3, blind).blob == want, k
+    top = "".join("%064x" % (v + ((1 << 256) - 1 - v) // o.R_MOD * o.R_MOD) for v in values)   # the largest representative
+    assert pk_d.ProveHex(top.encode(), nw + 3, blind).blob == want
+    bad = text[:70] + "x" + text[71:]
+    with pytest.raises(zk.B200zkError) as e:
+        pk_d.ProveHex(bad.encode(), nw + 3, blind)
+    assert e.value.code == -3
+    wrong = list(values)
+    wrong[order[200]] += 1
+    with pytest.raises(zkp.UnsatisfiedConstraint):
+        pk_d.ProveHex("".join("%064x" % v for v in wrong).encode(), nw + 3, blind)
+    assert pk_d.Prove(o.fr_to_mont_bytes(x), blind).blob == want
+    pk_d.close()
+    srs_d.close()
