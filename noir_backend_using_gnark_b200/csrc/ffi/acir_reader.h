@@ -158,6 +158,19 @@ inline std::vector<Fe4> felts_from_hex(Span h) {
   return out;
 }
 
+// hex.DecodeString's acceptance test without producing the bytes (threaded)
+inline bool hex_is_valid(Span s) {
+  if (s.n % 2) return false;
+  const int8_t* T = hex_table();
+  std::atomic<bool> bad(false);
+  parallel_for(s.n, (size_t)1 << 20, [&](size_t b, size_t e) {
+    int acc = 0;
+    for (size_t i = b; i < e; i++) acc |= T[(uint8_t)s.p[i]];
+    if (acc < 0) bad.store(true);
+  });
+  return !bad.load();
+}
+
 // ------------------------------------------------------------------------------------------------ content hash
 // 128-bit non-cryptographic digest of a payload (cache key for parsed circuits and device keys).  A collision could
 // only make this process prove with the key of another circuit it has itself submitted; the proof would then fail

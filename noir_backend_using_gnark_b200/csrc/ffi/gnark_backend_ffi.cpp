@@ -471,6 +471,42 @@ size_t pk_stream_bytes(const Keyed& k) {  // ProvingKey.WriteTo size
   return k.vk_bytes.size() + 2 * (8 + 5 * 32) + 9 * (4 + 32 * k.n) + 4 + 8 * 3 * k.n;
 }
 
+// the 9 blinding scalars of plonk.Prove: fr.SetRandom draws (their limbs are the Montgomery form)
+void draw_blinding(Fe4 blinding[9]) {
+  if (const char* seed = getenv("B200ZK_BLINDING_SEED")) {
+    uint64_t st = strtoull(seed, nullptr, 0);
+    for (int i = 0; i < 9;) {
+      Fe4 v;
+      for (int j = 0; j < 4; j++) {
+        st += 0x9E3779B97F4A7C15ULL;
+        uint64_t z = st;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+        v.l[j] = z ^ (z >> 31);
+      }
+      v.l[3] &= 0x3fffffffffffffffULL;
+      if (!host::geq(v.l, HFR.m)) blinding[i++] = v;
+    }
+    return;
+  }
+  FILE* ur = fopen("/dev/urandom", "rb");
+  if (!ur) fatal("cannot open /dev/urandom");
+  for (int i = 0; i < 9; i++) blinding[i] = random_fr(ur);
+  fclose(ur);
+}
+
+// hex(u32-BE count || 32-byte elements) with a complete body: the count, else false (short / empty payloads take the
+// host path, which reproduces the reference's ignored UnmarshalBinary error)
+bool felts_count(Span h, size_t* count) {
+  if (h.n % 2 || h.n < 8) return false;
+  uint8_t head[4];
+  if (!hex_decode_into(Span{h.p, 8}, head)) return false;
+  const size_t n = ((size_t)head[0] << 24) | ((size_t)head[1] << 16) | ((size_t)head[2] << 8) | head[3];
+  if (n == 0 || (h.n - 8) / 64 < n) return false;
+  *count = n;
+  return true;
+}
+
 }  // namespace
 
 // ================================================================================================ exports
@@ -556,42 +592,6 @@ struct PlonkPreprocess_return PlonkPreprocess(GoString acirJSON, GoString encode
   return r;
 }
 
-// the 9 blinding scalars of plonk.Prove: fr.SetRandom draws (their limbs are the Montgomery form)
-static void draw_blinding(Fe4 blinding[9]) {
-  if (const char* seed = getenv("B200ZK_BLINDING_SEED")) {
-    uint64_t st = strtoull(seed, nullptr, 0);
-    for (int i = 0; i < 9;) {
-      Fe4 v;
-      for (int j = 0; j < 4; j++) {
-        st += 0x9E3779B97F4A7C15ULL;
-        uint64_t z = st;
-        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
-        z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
-        v.l[j] = z ^ (z >> 31);
-      }
-      v.l[3] &= 0x3fffffffffffffffULL;
-      if (!host::geq(v.l, HFR.m)) blinding[i++] = v;
-    }
-    return;
-  }
-  FILE* ur = fopen("/dev/urandom", "rb");
-  if (!ur) fatal("cannot open /dev/urandom");
-  for (int i = 0; i < 9; i++) blinding[i] = random_fr(ur);
-  fclose(ur);
-}
-
-// hex(u32-BE count || 32-byte elements) with a complete body: the count, else false (short / empty payloads take the
-// host path, which reproduces the reference's ignored UnmarshalBinary error)
-static bool felts_count(Span h, size_t* count) {
-  if (h.n % 2 || h.n < 8) return false;
-  uint8_t head[4];
-  if (!hex_decode_into(Span{h.p, 8}, head)) return false;
-  const size_t n = ((size_t)head[0] << 24) | ((size_t)head[1] << 16) | ((size_t)head[2] << 8) | head[3];
-  if (n == 0 || (h.n - 8) / 64 < n) return false;
-  *count = n;
-  return true;
-}
-
 char* PlonkProveWithPK(GoString acirJSON, GoString encodedValues, GoString encodedProvingKey) {  // main.go:24-37
   Trace trace("PlonkProveWithPK");
   const Span payload = span_of(encodedValues);
@@ -663,13 +663,26 @@ uint8_t PlonkVerifyWithVK(GoString acirJSON, GoString encodedProof, GoString enc
                           GoString encodedVerifyingKey) {  // main.go:44-56, plonk.go:29-51
   Trace trace("PlonkVerifyWithVK");
   ParsedProof proof = parse_proof(hex_decode(span_of(encodedProof)));
-  std::vector<Fe4> values = felts_from_hex(span_of(encodedPublicInputs));
   ParsedVk vk = parse_vk(hex_decode(span_of(encodedVerifyingKey)));
+  // DeserializeFelts: the whole payload must be hex, but only the values that turn out to be public are needed
+  const Span payload = span_of(encodedPublicInputs);
+  size_t nvalues = 0;
+  std::vector<Fe4> values;
+  const bool lazy = felts_count(payload, &nvalues);
+  if (lazy) {
+    if (!hex_is_valid(payload)) fatal("encoding/hex: invalid byte");
+  } else {
+    values = felts_from_hex(payload);
+    nvalues = values.size();
+  }
   trace("payloads decoded");
   State::Entry& entry = circuit_entry(span_of(acirJSON));
-  Keyed& k = keyed(entry, values.size());  // only to learn which values are public (plonk.go:30)
+  Keyed& k = keyed(entry, nvalues);  // only to learn which values are public (plonk.go:30)
   std::vector<Fe4> pub(k.plan.nb_public);
-  for (unsigned i = 0; i < k.plan.nb_public; i++) pub[i] = values[k.plan.solution_src[i]];
+  for (unsigned i = 0; i < k.plan.nb_public; i++) {
+    const size_t src = k.plan.solution_src[i];
+    pub[i] = lazy ? felt_from_hex(Span{payload.p + 8 + 64 * src, 64}) : values[src];
+  }
   trace("circuit read / found");
   ensure_srs();  // vk.InitKZG(srs): the G2 elements live in the SRS file
   const bool ok = plonk_verify(proof, vk, pub, state().g2);
