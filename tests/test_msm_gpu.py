@@ -310,3 +310,42 @@ def test_host_scalar_msm_split_for_copy_overlap(ctx, chunks):
     finally:
         lib.b200zk_msm_set_host_chunks(ctx.handle, 0)
         srs.close()
+
+
+def test_maximum_sweep_size_2_26(ctx):
+    """2^26 points (the top of BASELINE.json's MSM sweep): no oracle at this size — classic windows, the window table
+    and the sum of four point-range shards are three different summation orders and must agree byte for byte; with all
+    scalars equal to s the result must also be the closed form s*(alpha^n - 1)/(alpha - 1)*G."""
+    import torch
+
+    n = 1 << 26
+    alpha_int = o.random_fr(1, 0xB2000005)[0]
+    srs = zk.SRS.NewSRS(n, o.fr_to_mont_bytes([alpha_int]), ctx)
+    sc = torch.randint(0, 256, (n * 32,), dtype=torch.uint8, device="cuda")
+    sc.view(n, 32)[:, 31] &= 0x1F                                # < 2^253 < r: valid Montgomery images
+    torch.cuda.synchronize()
+    out = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    zk.MultiExp(srs, sc, n=n, out=out)
+    ctx.sync()
+    classic = out.cpu().numpy().tobytes()
+    srs.precompute()
+    zk.MultiExp(srs, sc, n=n, out=out)
+    ctx.sync()
+    table = out.cpu().numpy().tobytes()
+    q = n // 4
+    parts = torch.empty(4 * 128, dtype=torch.uint8, device="cuda")
+    for i in range(4):
+        zk.MultiExp(srs, sc[i * q * 32:(i + 1) * q * 32], n=q, first_base=i * q, out=parts[128 * i:128 * (i + 1)], partial=True)
+    res = zk.SumPartials(ctx, parts)
+    ctx.sync()
+    assert classic == table == res.cpu().numpy().tobytes() and classic != b"\0" * 64
+    s = 0x0123456789ABCDEF0123456789ABCDEF % o.R_MOD
+    eq = torch.from_numpy(np.frombuffer(o.fr_to_mont_bytes([s]), dtype=np.uint8).copy()).cuda().repeat(n)
+    torch.cuda.synchronize()
+    zk.MultiExp(srs, eq, n=n, out=out)
+    ctx.sync()
+    geo = (pow(alpha_int, n, o.R_MOD) - 1) * pow(alpha_int - 1, -1, o.R_MOD) % o.R_MOD
+    assert out.cpu().numpy().tobytes() == o.g1_to_bytes([o.g1_mul(o.G1_GEN, s * geo % o.R_MOD)])
+    srs.close()
+    del sc, eq, parts
+    torch.cuda.empty_cache()

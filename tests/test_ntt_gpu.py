@@ -212,3 +212,44 @@ def test_large_sizes_roundtrip(ctx):
         ctx.sync()
         assert torch.equal(y, x)
         del x, y
+
+
+def test_maximum_size_2_28(ctx):
+    """2^28 = the 2-adicity of BN254 fr, the largest domain gnark can build (BASELINE.json config 5).  No oracle at this
+    size (8 GiB of input): the transform of a single non-zero coefficient c*X^k must be the geometric sequence
+    c*w^(k*j) (sampled against Python big integers), and FFTInverse(FFT(x)) must return a random x, coset included."""
+    import torch
+
+    log2n = 28
+    n = 1 << log2n
+    d = zk.Domain(n, ctx)
+    w = pow(o.FR_ROOT_2_28, 1, o.R_MOD)                       # generator of the 2^28 domain itself
+    rng = np.random.default_rng(28)
+    k, c = int(rng.integers(1, n)), 0x1234567890ABCDEF
+    x = torch.zeros(n * 32, dtype=torch.uint8, device="cuda")
+    x[k * 32:(k + 1) * 32] = torch.from_numpy(np.frombuffer(o.fr_to_mont_bytes([c]), dtype=np.uint8).copy()).cuda()
+    torch.cuda.synchronize()
+    d.FFT(x, zk.DIF, False)                                    # natural in -> bit-reversed out
+    ctx.sync()
+    for j in [0, 1, 2, n - 1, n // 2] + [int(v) for v in rng.integers(0, n, 40)]:
+        pos = int(format(j, "028b")[::-1], 2)
+        got = bytes(x[pos * 32:(pos + 1) * 32].cpu().numpy())
+        assert got == o.fr_to_mont_bytes([c * pow(w, k * j, o.R_MOD) % o.R_MOD]), j
+    d.FFTInverse(x, zk.DIT, False)
+    ctx.sync()
+    nz = torch.nonzero(x.view(torch.int64)).flatten()
+    assert nz.numel() > 0 and int(nz.min()) // 4 == k and int(nz.max()) // 4 == k      # back to c*X^k exactly
+    del x
+    # random input (valid Montgomery images: top three bits cleared -> < 2^253 < r), coset round trip
+    y = torch.randint(0, 256, (n * 32,), dtype=torch.uint8, device="cuda")
+    y.view(n, 32)[:, 31] &= 0x1F
+    ref = y.clone()
+    torch.cuda.synchronize()
+    d.FFT(y, zk.DIF, True)
+    ctx.sync()
+    assert not torch.equal(y, ref)
+    d.FFTInverse(y, zk.DIT, True)
+    ctx.sync()
+    assert torch.equal(y, ref)
+    del y, ref
+    torch.cuda.empty_cache()
