@@ -905,6 +905,36 @@ class CProver:
         self.vk_points = np.frombuffer(o.g1_to_bytes(vk.S + [vk.Ql, vk.Qr, vk.Qm, vk.Qo, vk.Qk]), dtype=np.uint8).copy()
         del dom
 
+    @classmethod
+    def from_arrays(cls, log2n: int, log2n_big: int, nb_public: int, nb_wires: int, polys, perm, lro, vk_points,
+                    srs_g1_bytes, nthreads: int = 0) -> "CProver":
+        """The same prover for sizes the Python setup cannot reach: `polys` are the 9 key polynomials as Montgomery
+        byte images (Ql Qr Qm Qo CQk LQk S1 S2 S3); the Lagrange-coset forms are derived here with the C NTT, as
+        gnark does when it loads a key."""
+        import ctypes as C
+        from types import SimpleNamespace
+
+        self = object.__new__(cls)
+        self.C, self.lib = C, cref.load()
+        n, N4 = 1 << log2n, 1 << log2n_big
+        self.polys = [np.frombuffer(bytes(p), dtype=np.uint8).copy() for p in polys]
+        th = nthreads or cref.ncores()
+
+        def coset(canonical: np.ndarray) -> np.ndarray:
+            buf = np.zeros(N4 * 32, dtype=np.uint8)
+            buf[: canonical.size] = canonical
+            return np.frombuffer(cref.ntt(buf, log2n_big, 0, o.DIF, 1, th), dtype=np.uint8).copy()
+
+        lone = np.tile(np.frombuffer(o.fr_to_mont_bytes([pow(n, -1, R)]), dtype=np.uint8), n)
+        self.cosets = [coset(self.polys[i]) for i in (0, 1, 2, 3, 6, 7, 8)] + [coset(lone)]
+        self.perm = np.ascontiguousarray(perm, dtype=np.int64)
+        self.lro = np.ascontiguousarray(lro, dtype=np.uint32)
+        self.vk_points = np.frombuffer(bytes(vk_points), dtype=np.uint8).copy()
+        self.cs = SimpleNamespace(nb_public=nb_public, nb_secret=nb_wires - nb_public)
+        self.pk = SimpleNamespace(n=n, n_big=N4)
+        self.srs = SimpleNamespace(g1_bytes=np.ascontiguousarray(srs_g1_bytes))
+        return self
+
     def prove_blob(self, full_witness, blinding_images: bytes, nthreads: int = 0) -> bytes:
         C = self.C
         sol = np.frombuffer(o.fr_to_mont_bytes(full_witness), dtype=np.uint8).copy() if not isinstance(full_witness, np.ndarray) else full_witness

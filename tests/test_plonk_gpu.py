@@ -180,3 +180,46 @@ def test_prove_from_hex_text_matches_prove(ctx):
     assert pk_d.Prove(o.fr_to_mont_bytes(x), blind).blob == want
     pk_d.close()
     srs_d.close()
+
+
+def test_2_20_rows_byte_identical_to_the_c_port(ctx):
+    """BASELINE.json config 2: 2^20 rows, seeded blinding, proof byte identity.  The Python oracle cannot set up a
+    circuit this large, so the C port of the prover is fed the key polynomials downloaded from the device (their
+    parity with the oracle's setup is established at the sizes the oracle reaches) plus a permutation rebuilt here by
+    gnark's sequential rule; everything the prover itself computes is then compared byte for byte, and the proof is
+    checked by the independent pairing verifier."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    from prove_bench import synthetic
+
+    log2n = 20
+    n = 1 << log2n
+    c = synthetic(log2n)
+    alpha_img = o.fr_to_mont_bytes([ALPHA])
+    srs_d = zk.SRS.NewSRS(n + 3, alpha_img, ctx).precompute()
+    pk_d = zkp.ProvingKey.SetupRaw(srs_d, log2n, log2n + 2, 1, c["nb_wires"], c["ql"], c["qr"], c["qm"], c["qo"], c["qk"],
+                                   c["lro"], ctx)
+    blind = blinding_bytes(0xB2000006)
+    proof = pk_d.Prove(c["sol"], blind)
+    # buildPermutation, sequentially: each position points to the previous one holding the same wire, the first to the last
+    lro = c["lro"].tolist()
+    perm, cycle = [-1] * (3 * n), [-1] * c["nb_wires"]
+    for i, wire in enumerate(lro):
+        if cycle[wire] != -1:
+            perm[i] = cycle[wire]
+        cycle[wire] = i
+    for i, wire in enumerate(lro):
+        if perm[i] == -1:
+            perm[i] = cycle[wire]
+    assert np.array_equal(np.asarray(perm, dtype=np.int64), pk_d.permutation)
+    cp = pl.CProver.from_arrays(log2n, log2n + 2, 1, c["nb_wires"], [pk_d.poly(i) for i in range(9)], perm, c["lro"],
+                                b"".join(pk_d.vk_points), np.frombuffer(srs_d.download(), dtype=np.uint8))
+    blob = cp.prove_blob(np.ascontiguousarray(c["sol"]), blind.tobytes())
+    assert proof.blob == blob
+    S = [o.g1_from_bytes(b)[0] for b in pk_d.vk_points]
+    vk = pl.VerifyingKey(n, pow(n, -1, o.R_MOD), o.Domain(n).generator, 1, 5, S[:3], S[3], S[4], S[5], S[6], S[7])
+    assert pl.verify(pl.Proof.from_bytes(proof.to_gnark_bytes()), vk, [c["x0"]], (pl.G2_GEN, pl.g2_mul(pl.G2_GEN, ALPHA)))
+    pk_d.close()
+    srs_d.close()
