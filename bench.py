@@ -201,36 +201,37 @@ def run_reference(args, rank: int, world: int) -> None:
 def prove_cpu_baseline(ctx, sample_log2: int) -> dict:
     """CPU arm of the prove metric on a bounded sample: the C port of the prover (oracle/bn254_ref.c, all host
     cores) on a 2^sample_log2-row chain circuit, next to the CUDA prover on the SAME circuit, SRS and blinding —
-    whose proof bytes must be identical (three-way parity: Python oracle == C port == CUDA is covered by the tests)."""
+    whose proof bytes must be identical.  The C port is handed the key polynomials of the device key (what gnark holds
+    after ProvingKey.ReadFrom) and derives the coset forms itself; setup parity is covered by the tests."""
     import numpy as np
 
     import noir_backend_using_gnark_b200 as zk
     from noir_backend_using_gnark_b200 import plonk as zkp
-    from oracle import bn254 as o
     from oracle import cref
     from oracle import plonk as pl
 
-    gates = (1 << sample_log2) - 1
-    cs_o, x = pl.synthetic_chain_circuit(gates, 0xB2000004)
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    from prove_bench import synthetic
+
+    n = 1 << sample_log2
+    c = synthetic(sample_log2)
     alpha = SEED_SRS * 0x9E3779B97F4A7C15 % zkp.R_MOD
-    srs_o = pl.SRS((1 << sample_log2) + 3, alpha)
-    pk_o = pl.setup(cs_o, srs_o)
-    cp = pl.CProver(cs_o, pk_o, srs_o)
-    blind = random_fr_images(9, 0xB2000006).tobytes()
-    sol = np.frombuffer(o.fr_to_mont_bytes(x), dtype=np.uint8).copy()
-    cores = cref.ncores()
-    t0 = time.perf_counter()
-    blob_cpu = cp.prove_blob(sol, blind, cores)
-    cpu_ms = (time.perf_counter() - t0) * 1e3
-    g = cs_o.gates
-    cs_p = zkp.SparseR1CS(cs_o.nb_public, cs_o.nb_secret, [t.ql for t in g], [t.qr for t in g], [t.qm for t in g],
-                          [t.qo for t in g], [t.qk for t in g], [t.a for t in g], [t.b for t in g], [t.c for t in g])
-    srs_d = zk.SRS.NewSRS((1 << sample_log2) + 3, zkp.fr_to_mont([alpha]), ctx).precompute()
-    pk_d = zkp.ProvingKey.Setup(cs_p, srs_d, ctx)
+    srs_d = zk.SRS.NewSRS(n + 3, zkp.fr_to_mont([alpha]), ctx).precompute()
+    pk_d = zkp.ProvingKey.SetupRaw(srs_d, sample_log2, sample_log2 + 2, 1, c["nb_wires"], c["ql"], c["qr"], c["qm"], c["qo"],
+                                   c["qk"], c["lro"], ctx)
+    blind = random_fr_images(9, 0xB2000006)
+    sol = np.ascontiguousarray(c["sol"])
     pk_d.Prove(sol, blind)
     t0 = time.perf_counter()
     proof_gpu = pk_d.Prove(sol, blind)
     gpu_ms = (time.perf_counter() - t0) * 1e3
+    cores = cref.ncores()
+    cp = pl.CProver.from_arrays(sample_log2, sample_log2 + 2, 1, c["nb_wires"], [pk_d.poly(i) for i in range(9)],
+                                pk_d.permutation, c["lro"], b"".join(pk_d.vk_points),
+                                np.frombuffer(srs_d.download(), dtype=np.uint8), cores)
+    t0 = time.perf_counter()
+    blob_cpu = cp.prove_blob(sol, blind.tobytes(), cores)
+    cpu_ms = (time.perf_counter() - t0) * 1e3
     same = proof_gpu.blob == blob_cpu
     pk_d.close()
     srs_d.close()
@@ -432,7 +433,7 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
         srs.close()          # free the 2^24 window table before the prover allocates its arena
         del d_sc
         torch.cuda.empty_cache()
-        prove_info = run_prove(ctx, args.prove_log2n, rank, world, 0 if args.no_cpu else 16)
+        prove_info = run_prove(ctx, args.prove_log2n, rank, world, 0 if args.no_cpu else 20)
 
     if rank != 0:
         if world > 1:
