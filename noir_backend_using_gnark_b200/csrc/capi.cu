@@ -343,6 +343,12 @@ int b200zk_msm_g1(b200zk_ctx* ctx, const b200zk_bases* bases, const void* scalar
   return B200ZK_OK;
 }
 
+int b200zk_msm_set_small_path(b200zk_ctx* ctx, int on) {
+  if (!ctx) return B200ZK_ERR_BAD_ARG;
+  ctx->msm_no_tiny = on ? 0 : 1;
+  return B200ZK_OK;
+}
+
 int b200zk_msm_set_host_chunks(b200zk_ctx* ctx, int chunks) {
   if (!ctx || chunks < 0 || chunks > 8) return B200ZK_ERR_BAD_ARG;
   ctx->msm_host_chunks = chunks;

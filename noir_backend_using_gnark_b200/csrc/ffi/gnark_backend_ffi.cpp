@@ -36,7 +36,10 @@ struct Trace {
   bool on;
   double t0, last;
   const char* fn;
-  explicit Trace(const char* f) : on(getenv("B200ZK_FFI_TRACE") != nullptr), t0(now_ms()), last(t0), fn(f) {}
+  explicit Trace(const char* f) : on(false), t0(now_ms()), last(t0), fn(f) {
+    const char* e = getenv("B200ZK_FFI_TRACE");
+    on = e && *e && strcmp(e, "0") != 0;
+  }
   void operator()(const char* what) {
     if (!on) return;
     const double t = now_ms();

@@ -29,6 +29,7 @@ static constexpr int CHUNK_LOG = 5;
 static constexpr int CHUNK = 1 << CHUNK_LOG;   // buckets per running-sum chunk
 static constexpr int BIG_CHUNK = 8192;         // sorted entries per CTA in the long-run path
 static constexpr int BIG_THREADS = 256;
+static constexpr size_t TINY_MAX_TERMS = (size_t)1 << 17;  // (points x windows) up to which the bucket pipeline is skipped
 static constexpr int MAX_WINDOWS = 64;
 static constexpr int SLICE = 1024;             // chunk results per CTA in the bit-plane sums
 static constexpr int MAX_PLANES = 24;
@@ -472,6 +473,57 @@ __global__ void __launch_bounds__(256) msm_reduce_r3_kernel(const void* __restri
 }
 
 // ---------------------------------------------------------------------------------------------------
+// 5b. small MSMs against a window table (the sizes of the reference's own test circuits: tens to thousands of
+//     points).  Bucketing has nothing to amortise there and the pipeline above is ~17 latency-bound launches, so
+//     every (point, window) pair becomes one thread: digit * T[window][point] by double-and-add over the <= 13-bit
+//     digit (unsigned windows: no carries), summed by a shared-memory tree per CTA and by one final CTA.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BIG_THREADS) msm_tiny_kernel(const void* __restrict__ table,
+                                                               const uint4* __restrict__ scalars, unsigned n, MsmShape sh,
+                                                               void* __restrict__ partials) {
+  extern __shared__ uint4 big_smem[];
+  G1XYZZ* sh_pts = reinterpret_cast<G1XYZZ*>(big_smem);
+  const unsigned t = blockIdx.x * BIG_THREADS + threadIdx.x;
+  G1XYZZ acc = g1_xyzz_inf();
+  if (t < n * sh.W) {
+    const unsigned w = t / n, i = t - w * n;
+    const Fr s = load_scalar_regular(scalars, i);
+    const unsigned bit = sh.wstart[w], width = (unsigned)sh.wstart[w + 1] - bit;
+    const unsigned limb = bit >> 5, off = bit & 31;
+    unsigned d = 0;
+    if (width) {
+      const unsigned lo = s.l[limb], hi = limb + 1 < 8 ? s.l[limb + 1] : 0u;
+      d = (unsigned)((((uint64_t)hi << 32) | lo) >> off) & ((1u << width) - 1u);
+    }
+    if (d) {
+      const G1Affine pt = g1_load_affine(table, (size_t)w * sh.tab_stride + sh.first + i);
+      for (int b = 31 - __clz(d); b >= 0; b--) {
+        g1_double(acc);
+        if ((d >> b) & 1u) g1_add_mixed(acc, pt);
+      }
+    }
+  }
+  block_reduce_xyzz(acc, sh_pts);
+  if (threadIdx.x == 0) g1_store_xyzz(partials, blockIdx.x, acc);
+}
+
+__global__ void __launch_bounds__(BIG_THREADS) msm_tiny_final_kernel(const void* __restrict__ partials, unsigned count,
+                                                                     void* __restrict__ out, int out_kind) {
+  extern __shared__ uint4 big_smem[];
+  G1XYZZ* sh_pts = reinterpret_cast<G1XYZZ*>(big_smem);
+  G1XYZZ acc = g1_xyzz_inf();
+  for (unsigned k = threadIdx.x; k < count; k += BIG_THREADS) {
+    G1XYZZ q = g1_load_xyzz(partials, k);
+    g1_add(acc, q);
+  }
+  block_reduce_xyzz(acc, sh_pts);
+  if (threadIdx.x == 0) {
+    if (out_kind == 0) g1_store_affine(out, 0, g1_to_affine(acc));
+    else g1_store_xyzz(out, 0, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // 6. window Horner (classic mode) + normalisation
 // ---------------------------------------------------------------------------------------------------
 __global__ void msm_final_kernel(const void* __restrict__ set_sums, MsmShape sh, void* __restrict__ out, int out_kind) {
@@ -583,7 +635,7 @@ int msm_precompute_run(b200zk_ctx* ctx, b200zk_bases* bases, int c_req) {
   if (!bases || !bases->dev) return B200ZK_ERR_BAD_ARG;
   if (bases->table) return B200ZK_OK;
   const size_t n = bases->n;
-  if (n < 1024) return B200ZK_OK;  // not worth it: the classic path is used
+  if (n == 0) return B200ZK_OK;
   unsigned lg = 0;
   while (((size_t)1 << (lg + 1)) <= n) lg++;
   // number of windows from the size (or from a requested maximum width c_req): W windows of 255/W bits (+1 for the
@@ -663,6 +715,24 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
   }
   MsmShape sh;
   memset(&sh, 0, sizeof(sh));
+  if (bases->table && !ctx->forced_window && !ctx->msm_no_tiny && n * (size_t)bases->tab_W <= TINY_MAX_TERMS) {
+    // small problem: one thread per (point, window) term of the table, two launches
+    sh.c = bases->tab_c;
+    sh.W = bases->tab_W;
+    sh.tab_stride = (unsigned)bases->n;
+    sh.first = (unsigned)first_base;
+    memcpy(sh.wstart, bases->tab_wstart, sizeof(sh.wstart));
+    const unsigned terms = (unsigned)(n * sh.W);
+    const unsigned blocks = (terms + BIG_THREADS - 1) / BIG_THREADS;
+    B200ZK_TRY(ensure(ctx, ctx->msm_big, (size_t)blocks * 128));
+    const size_t shm = (size_t)BIG_THREADS * sizeof(G1XYZZ);
+    PhaseTimer pt(ctx, PH_MSM_ACCUMULATE);
+    msm_tiny_kernel<<<blocks, BIG_THREADS, shm, st>>>(bases->table, (const uint4*)scalars_dev, (unsigned)n, sh, ctx->msm_big.p);
+    B200ZK_LAUNCH_CHECK(ctx, "msm_tiny_kernel");
+    msm_tiny_final_kernel<<<1, BIG_THREADS, shm, st>>>(ctx->msm_big.p, blocks, out_dev, out_kind);
+    B200ZK_LAUNCH_CHECK(ctx, "msm_tiny_final_kernel");
+    return B200ZK_OK;
+  }
   const bool use_table = bases->table && !ctx->forced_window && n * 16 >= bases->n;
   const void* base_ptr;
   if (use_table) {

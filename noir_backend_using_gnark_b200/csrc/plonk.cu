@@ -474,14 +474,30 @@ struct SmallMsmArgs {
   FrArg scalars[8];        // regular form
   unsigned count;
 };
-__global__ void k_small_msm(SmallMsmArgs a, void* out) {
+// two independent digests in one launch (one warp-sized CTA each): they are latency-bound, so running them side by
+// side halves their contribution to the critical path of small circuits
+__global__ void k_small_msm(SmallMsmArgs a0, void* out0, SmallMsmArgs a1, void* out1) {
+  const SmallMsmArgs& a = blockIdx.x == 0 ? a0 : a1;
+  void* out = blockIdx.x == 0 ? out0 : out1;
   const unsigned lane = threadIdx.x & 31;
+  // 4-bit fixed windows: the lane's multiples 1P..15P live in shared memory, so the 256 doublings are followed by 64
+  // additions instead of one (divergent) addition per bit
+  __shared__ G1XYZZ multiples[8][15];
   G1XYZZ acc = g1_xyzz_inf();
   if (lane < a.count) {
-    G1Affine p = g1_load_affine(a.points[lane], 0);
-    for (int b = 255; b >= 0; b--) {
+    const G1Affine p = g1_load_affine(a.points[lane], 0);
+    G1XYZZ m = g1_xyzz_inf();
+    for (int k = 0; k < 15; k++) {
+      g1_add_mixed(m, p);
+      multiples[lane][k] = m;
+    }
+    for (int w = 63; w >= 0; w--) {
       g1_double(acc);
-      if ((a.scalars[lane].l[b >> 5] >> (b & 31)) & 1u) g1_add_mixed(acc, p);
+      g1_double(acc);
+      g1_double(acc);
+      g1_double(acc);
+      const unsigned d = (a.scalars[lane].l[w >> 3] >> (4 * (w & 7))) & 15u;
+      if (d) g1_add(acc, multiples[lane][d - 1]);
     }
   }
   for (int d = 16; d > 0; d >>= 1) {
@@ -1020,11 +1036,12 @@ static int prove_impl(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solution
   // the opening MSM below instead of sitting on the critical path.
   B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
   B200ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+  SmallMsmArgs sm_lin, sm_fold;
   {
     // digest of the linearised polynomial from the commitments it is a linear combination of (what the verifier
     // does; equal to kzg.Commit(lin) because the commitment is linear) instead of a full (n+3)-point MSM:
     //   l*[Ql] + r*[Qr] + l*r*[Qm] + o*[Qo] + [Qk] + alpha*c1*[S3] + (alpha*c2 + lag)*[Z]
-    SmallMsmArgs sm;
+    SmallMsmArgs& sm = sm_lin;
     char* vkd = (char*)pk->points + 64 * 16;  // device copy of the vk points (uploaded at setup)
     const void* pp[7] = {vkd + 64 * 3, vkd + 64 * 4, vkd + 64 * 5, vkd + 64 * 6, vkd + 64 * 7, vkd + 64 * 2,
                          (char*)pk->points + 64 * 11};
@@ -1036,21 +1053,20 @@ static int prove_impl(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solution
     sm.points[7] = pp[0];
     sm.scalars[7] = to_arg(Fe4{{0, 0, 0, 0}});
     sm.count = 7;
-    k_small_msm<<<1, 32, 0, ctx->side>>>(sm, (char*)pk->points + 64 * 0);  // slot 0: linearised polynomial digest
-    B200ZK_LAUNCH_CHECK(ctx, "k_small_msm");
   }
   {
     // foldedHDigest = H0 + zpm*H1 + zpm^2*H2
-    SmallMsmArgs sm;
+    SmallMsmArgs& sm = sm_fold;
     const Fe4 ss[3] = {HFR.one, zpm, M(zpm, zpm)};
     for (int i = 0; i < 8; i++) {
       sm.points[i] = (char*)pk->points + 64 * (12 + (i < 3 ? i : 0));
       sm.scalars[i] = to_arg(i < 3 ? host::from_mont(HFR, ss[i]) : Fe4{{0, 0, 0, 0}});
     }
     sm.count = 3;
-    k_small_msm<<<1, 32, 0, ctx->side>>>(sm, (char*)pk->points + 64 * 1);
-    B200ZK_LAUNCH_CHECK(ctx, "k_small_msm");
   }
+  // slot 0: linearised polynomial digest, slot 1: folded H digest
+  k_small_msm<<<2, 32, 0, ctx->side>>>(sm_lin, (char*)pk->points + 64 * 0, sm_fold, (char*)pk->points + 64 * 1);
+  B200ZK_LAUNCH_CHECK(ctx, "k_small_msm");
   B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side));
 
   // P14: opening of Z at w*zeta

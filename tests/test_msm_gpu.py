@@ -349,3 +349,42 @@ def test_maximum_sweep_size_2_26(ctx):
     srs.close()
     del sc, eq, parts
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 33, 100, 600, 1000, 4097, 6000])
+def test_small_msm_path_with_window_table(ctx, n):
+    """With a window table, MSMs of the size of the reference's own test circuits take a two-launch path (one thread
+    per (point, window) term).  Same result as the oracle, as the bucket pipeline on the same table and as classic
+    windows — including infinity bases, duplicate points, 0 / 1 / -1 scalars, cancellation and sub-ranges."""
+    lib = zk.load()
+    pts = structured(n).copy()
+    vals = o.random_fr(n, 0xB2000001 + n)
+    if n >= 33:
+        pts[5 * 64: 6 * 64] = 0
+        pts[9 * 64: 10 * 64] = pts[8 * 64: 9 * 64]
+        vals[0], vals[1], vals[2], vals[3] = 0, 1, o.R_MOD - 1, (1 << 253) % o.R_MOD
+        vals[8] = vals[9]
+        pts[12 * 64: 13 * 64] = pts[11 * 64: 12 * 64]
+        vals[12] = o.R_MOD - vals[11]                                  # cancels point 11
+    sc = np.frombuffer(o.fr_to_mont_bytes(vals), dtype=np.uint8)
+    want = cref.msm(pts, sc, n, nthreads=4)
+    srs = zk.SRS(pts, ctx)
+    try:
+        assert zk.MultiExp(srs, sc) == want                             # classic windows
+        srs.precompute()
+        assert zk.MultiExp(srs, sc) == want                             # small path
+        lib.b200zk_msm_set_small_path(ctx.handle, 0)
+        assert zk.MultiExp(srs, sc) == want                             # bucket pipeline on the same table
+        lib.b200zk_msm_set_small_path(ctx.handle, 1)
+        assert zk.MultiExp(srs, np.zeros(n * 32, dtype=np.uint8)) == b"\0" * 64
+        if n >= 100:
+            import torch
+
+            d = torch.from_numpy(sc.copy()).cuda()
+            out = torch.zeros(64, dtype=torch.uint8, device="cuda")
+            zk.MultiExp(srs, d[40 * 32: 90 * 32], n=50, first_base=40, out=out)
+            ctx.sync()
+            assert out.cpu().numpy().tobytes() == cref.msm(pts[40 * 64: 90 * 64], sc[40 * 32: 90 * 32], 50, nthreads=2)
+    finally:
+        lib.b200zk_msm_set_small_path(ctx.handle, 1)
+        srs.close()
