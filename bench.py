@@ -448,11 +448,14 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
         import subprocess
 
         try:
-            r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ffi_bench.py"), "16", "3"], capture_output=True,
-                               text=True, timeout=300)
-            ffi_info = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else {"error": r.stderr[-300:]}
-            ffi_info["api"] = ("PlonkPreprocess / PlonkProveWithPK / PlonkVerifyWithVK (GoString payloads: ACIR JSON, hex felts, "
-                               "hex keys) on a 2^16-row ACIR circuit; wall clock per call")
+            ffi_info = {"api": "PlonkPreprocess / PlonkProveWithPK / PlonkVerifyWithVK (GoString payloads: ACIR JSON, hex felts, "
+                               "hex keys); wall clock per call; 2^3 rows = the size of the reference's own test circuits "
+                               "(BASELINE.json config 1)"}
+            for lg in (3, 16):
+                r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ffi_bench.py"), str(lg), "5"],
+                                   capture_output=True, text=True, timeout=300)
+                ffi_info["rows_2^%d" % lg] = (json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0
+                                              else {"error": r.stderr[-300:]})
         except Exception as e:  # the headline numbers do not depend on this leg
             ffi_info = {"error": repr(e)}
 

@@ -75,7 +75,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
     # host-only C++ on top of the C ABI; found next to libb200zk.so through $ORIGIN
-    cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", str(FFI_LIB), str(FFI_SRC),
+    cmd = [os.environ.get("CXX", "g++"), "-O3", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", str(FFI_LIB), str(FFI_SRC),
            "-L" + str(LIBDIR), "-lb200zk", "-pthread", "-Wl,-rpath,$ORIGIN",
            "-Wl,--exclude-libs,ALL"]  # keep the statically linked parts of the C++ runtime out of the export table
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -129,6 +129,54 @@ inline G1 g1_add(const G1& a, const G1& b) {
   j = g1j_add_affine(j, b);
   return g1j_to_affine(j);
 }
+// sum_k scalars[k] * points[k] for a handful of points (the verifier's linear combinations): Straus with 4-bit
+// windows — the 252 doublings are shared, the multiples 1P..15P of every point are normalised to affine with one
+// inversion (Montgomery's trick) so that every addition in the main loop is a mixed one.  Scalars: Montgomery fr.
+inline G1J g1_msm_small(const std::vector<G1>& points, const std::vector<Fe4>& scalars_mont) {
+  const size_t n = points.size();
+  std::vector<G1J> jac(15 * n);
+  for (size_t k = 0; k < n; k++) {
+    G1J m = g1j_inf();
+    for (int d = 0; d < 15; d++) {
+      m = g1j_add_affine(m, points[k]);
+      jac[15 * k + d] = m;
+    }
+  }
+  // batch normalisation (entries with z = 0 stay at infinity)
+  std::vector<Fe4> prefix(jac.size());
+  Fe4 run = HFP.one;
+  for (size_t i = 0; i < jac.size(); i++) {
+    prefix[i] = run;
+    if (!host::is_zero(jac[i].z)) run = fp_mul(run, jac[i].z);
+  }
+  Fe4 inv_run = fp_inv(run);
+  std::vector<G1> table(jac.size());
+  for (size_t i = jac.size(); i-- > 0;) {
+    G1& t = table[i];
+    if (host::is_zero(jac[i].z)) {
+      t.x = t.y = fp_zero();
+      t.inf = true;
+      continue;
+    }
+    const Fe4 zi = fp_mul(inv_run, prefix[i]);
+    inv_run = fp_mul(inv_run, jac[i].z);
+    const Fe4 zi2 = fp_mul(zi, zi);
+    t.x = fp_mul(jac[i].x, zi2);
+    t.y = fp_mul(jac[i].y, fp_mul(zi2, zi));
+    t.inf = false;
+  }
+  std::vector<Fe4> sc(n);
+  for (size_t k = 0; k < n; k++) sc[k] = host::from_mont(HFR, scalars_mont[k]);
+  G1J acc = g1j_inf();
+  for (int w = 63; w >= 0; w--) {
+    for (int t = 0; t < 4; t++) acc = g1j_double(acc);
+    for (size_t k = 0; k < n; k++) {
+      const unsigned d = (unsigned)(sc[k].l[w / 16] >> (4 * (w % 16))) & 15u;
+      if (d) acc = g1j_add_affine(acc, table[15 * k + d - 1]);
+    }
+  }
+  return acc;
+}
 inline G1 g1_generator() { G1 g; g.x = HFP.one; g.y = fp_add(HFP.one, HFP.one); g.inf = false; return g; }
 
 // G1Affine.Bytes(): 32-byte BE X, flags 10 (smallest y) / 11 (largest y) / 01 (infinity)
@@ -474,28 +522,43 @@ inline void miller_step(F12& f, G2& r, const G2& s, const G1& p) {
   n.inf = false;
   r = n;
 }
-inline F12 miller_loop(const G2& q, const G1& p) {
-  if (q.inf || p.inf) return f12_one();
-  G2 r = q;
+// prod_i f_{6x+2,Q_i}(P_i) with the line corrections of the optimal ate pairing; the squaring of the accumulator is
+// shared by all pairs
+inline F12 miller_loop_product(const std::vector<std::pair<G1, G2>>& pairs) {
+  std::vector<const G1*> ps;
+  std::vector<const G2*> qs;
+  for (const auto& pq : pairs)
+    if (!pq.first.inf && !pq.second.inf) {
+      ps.push_back(&pq.first);
+      qs.push_back(&pq.second);
+    }
   F12 f = f12_one();
+  std::vector<G2> r;
+  for (auto q : qs) r.push_back(*q);
   // 6x+2 has 65 bits: bit 64 is the leading one, then ATE_LOOP_LO from bit 63 down
   for (int i = 63; i >= 0; i--) {
     f = f12_sqr(f);
-    miller_step(f, r, r, p);
-    if ((ATE_LOOP_LO >> i) & 1) miller_step(f, r, q, p);
+    for (size_t k = 0; k < r.size(); k++) {
+      miller_step(f, r[k], r[k], *ps[k]);
+      if ((ATE_LOOP_LO >> i) & 1) miller_step(f, r[k], *qs[k], *ps[k]);
+    }
   }
   const FrobTable& T = frob_table();
-  G2 q1, nq2;  // pi(Q) and -pi^2(Q) on the twist
-  q1.x = f2_mul(f2_conj(q.x), T.twist_x);
-  q1.y = f2_mul(f2_conj(q.y), T.twist_y);
-  q1.inf = false;
-  nq2.x = f2_mul(f2_conj(q1.x), T.twist_x);
-  nq2.y = f2_neg(f2_mul(f2_conj(q1.y), T.twist_y));
-  nq2.inf = false;
-  miller_step(f, r, q1, p);
-  miller_step(f, r, nq2, p);
+  for (size_t k = 0; k < r.size(); k++) {
+    const G2& q = *qs[k];
+    G2 q1, nq2;  // pi(Q) and -pi^2(Q) on the twist
+    q1.x = f2_mul(f2_conj(q.x), T.twist_x);
+    q1.y = f2_mul(f2_conj(q.y), T.twist_y);
+    q1.inf = false;
+    nq2.x = f2_mul(f2_conj(q1.x), T.twist_x);
+    nq2.y = f2_neg(f2_mul(f2_conj(q1.y), T.twist_y));
+    nq2.inf = false;
+    miller_step(f, r[k], q1, *ps[k]);
+    miller_step(f, r[k], nq2, *ps[k]);
+  }
   return f;
 }
+inline F12 miller_loop(const G2& q, const G1& p) { return miller_loop_product({{p, q}}); }
 // f^((p^12 - 1) / r) = ((f^(p^6 - 1))^(p^2 + 1))^((p^4 - p^2 + 1) / r); the last exponent is exactly
 // p^3 + (6x^2 + 1) p^2 - (36x^3 + 18x^2 + 12x - 1) p - (36x^3 + 30x^2 + 18x + 2) for the BN parameter x
 inline F12 final_exponentiation(const F12& f) {
@@ -555,9 +618,7 @@ inline F12 final_exponentiation(const F12& f) {
 }
 // prod_i e(P_i, Q_i) == 1
 inline bool pairing_product_is_one(const std::vector<std::pair<G1, G2>>& pairs) {
-  F12 f = f12_one();
-  for (const auto& pq : pairs) f = f12_mul(f, miller_loop(pq.second, pq.first));
-  return f12_eq(final_exponentiation(f), f12_one());
+  return f12_eq(final_exponentiation(miller_loop_product(pairs)), f12_one());
 }
 
 }  // namespace ffi

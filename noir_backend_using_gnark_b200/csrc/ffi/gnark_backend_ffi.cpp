@@ -369,13 +369,27 @@ struct Transcript {
   Fe4 finish() { h.finish(prev); have_prev = true; return host::set_bytes(HFR, prev); }
 };
 
-bool kzg_verify(const G1& commitment, const Fe4& z, const Fe4& v, const G1& Hq, const G2 g2[2]) {
-  // e(C - v G1 + z H, G2) * e(-H, alpha G2) == 1
-  G1J acc = g1j_inf();
-  acc = g1j_add_affine(acc, commitment);
-  acc = g1j_add_affine(acc, g1_neg(g1_mul(g1_generator(), v)));
-  acc = g1j_add_affine(acc, g1_mul(Hq, z));
-  return pairing_product_is_one({{g1j_to_affine(acc), g2[0]}, {g1_neg(Hq), g2[1]}});
+// kzg.BatchVerifyMultiPoints for the two openings of plonk.Verify: both checks
+//   e(C_i - v_i G1 + z_i H_i, G2) * e(-H_i, alpha G2) == 1
+// are folded with a challenge lambda derived from everything they depend on, so one product of two pairings decides:
+//   e(sum_i lambda^i (C_i + z_i H_i) - (sum_i lambda^i v_i) G1, G2) * e(-sum_i lambda^i H_i, alpha G2) == 1
+bool kzg_verify_two(const G1 C[2], const Fe4 z[2], const Fe4 v[2], const G1 Hq[2], const G2 g2[2]) {
+  Transcript t;
+  t.begin("lambda");
+  for (int i = 0; i < 2; i++) {
+    t.point(C[i]);
+    t.point(Hq[i]);
+    t.fr(z[i]);
+    t.fr(v[i]);
+  }
+  const Fe4 lambda = t.finish();
+  const Fe4 vsum = host::add(HFR, v[0], host::mul(HFR, lambda, v[1]));
+  G1J lhs = g1_msm_small({Hq[0], C[1], Hq[1], g1_generator()},
+                         {z[0], lambda, host::mul(HFR, lambda, z[1]), host::neg(HFR, vsum)});
+  lhs = g1j_add_affine(lhs, C[0]);
+  G1J hs = g1_msm_small({Hq[1]}, {lambda});
+  hs = g1j_add_affine(hs, Hq[0]);
+  return pairing_product_is_one({{g1j_to_affine(lhs), g2[0]}, {g1_neg(g1j_to_affine(hs)), g2[1]}});
 }
 
 bool plonk_verify(const ParsedProof& pr, const ParsedVk& vk, const std::vector<Fe4>& pub, const G2 g2[2]) {  // plonk.Verify
@@ -415,9 +429,7 @@ bool plonk_verify(const ParsedProof& pr, const ParsedVk& vk, const std::vector<F
   Fe4 lhs = S(A(A(lin_z, pi), t1), M(M(alpha, alpha), lag1));
   if (!fe_eq(lhs, M(q, zz))) return false;
   const Fe4 zpm = host::pow_u64(HFR, zeta, vk.size + 2);
-  G1J fh = g1_mul_j(pr.H[2], zpm);
-  fh = g1j_add_affine(fh, pr.H[1]);
-  fh = g1_mul_j(g1j_to_affine(fh), zpm);
+  G1J fh = g1_msm_small({pr.H[1], pr.H[2]}, {zpm, M(zpm, zpm)});  // H0 + zeta^(n+2) H1 + zeta^(2(n+2)) H2
   fh = g1j_add_affine(fh, pr.H[0]);
   const G1 folded_h = g1j_to_affine(fh);
   const Fe4 c_s3 = M(M(M(M(f1, f2), beta), alpha), zu);
@@ -425,24 +437,35 @@ bool plonk_verify(const ParsedProof& pr, const ParsedVk& vk, const std::vector<F
   c_z = A(host::neg(HFR, M(c_z, alpha)), M(M(alpha, alpha), lag1));
   const G1* lp[7] = {&vk.Ql, &vk.Qr, &vk.Qm, &vk.Qo, &vk.Qk, &vk.S[2], &pr.Z};
   const Fe4 ls[7] = {l, r, M(l, r), o, one, c_s3, c_z};
-  G1J lin = g1j_inf();
-  for (int i = 0; i < 7; i++) lin = g1j_add_affine(lin, g1_mul(*lp[i], ls[i]));
-  const G1 lin_digest = g1j_to_affine(lin);
+  std::vector<G1> lpts;
+  std::vector<Fe4> lsc;
+  for (int i = 0; i < 7; i++)
+    if (i != 4) {  // [Qk] enters with coefficient one
+      lpts.push_back(*lp[i]);
+      lsc.push_back(ls[i]);
+    }
+  const G1 lin_digest = g1j_to_affine(g1j_add_affine(g1_msm_small(lpts, lsc), vk.Qk));
   const G1 digests[7] = {folded_h, lin_digest, pr.LRO[0], pr.LRO[1], pr.LRO[2], vk.S[0], vk.S[1]};
   Transcript kz;
   kz.begin("gamma");
   kz.fr(zeta);
   for (int i = 0; i < 7; i++) kz.point(digests[i]);
   const Fe4 gk = kz.finish();
-  G1J fd = g1j_inf();
   Fe4 fe = {{0, 0, 0, 0}}, acc = one;
+  std::vector<G1> dpts;
+  std::vector<Fe4> dsc;
   for (int i = 0; i < 7; i++) {
-    fd = g1j_add_affine(fd, g1_mul(digests[i], acc));
+    if (i) {  // the first digest enters with gamma^0 = 1
+      dpts.push_back(digests[i]);
+      dsc.push_back(acc);
+    }
     fe = A(fe, M(pr.claimed[i], acc));
     acc = M(acc, gk);
   }
-  if (!kzg_verify(g1j_to_affine(fd), zeta, fe, pr.batched_H, g2)) return false;
-  return kzg_verify(pr.Z, M(zeta, vk.generator), zu, pr.zshift_H, g2);
+  const G1 Cs[2] = {g1j_to_affine(g1j_add_affine(g1_msm_small(dpts, dsc), digests[0])), pr.Z};
+  const Fe4 zs[2] = {zeta, M(zeta, vk.generator)}, vs[2] = {fe, zu};
+  const G1 Hs[2] = {pr.batched_H, pr.zshift_H};
+  return kzg_verify_two(Cs, zs, vs, Hs, g2);
 }
 
 // hex text written straight into the malloc'ed result (the pk of a 2^20-row circuit is 650 MB of hex)

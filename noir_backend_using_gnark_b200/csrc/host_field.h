@@ -83,32 +83,45 @@ inline Fe4 neg(const Field& F, const Fe4& a) {
   Fe4 z = {{0, 0, 0, 0}};
   return sub(F, z, a);
 }
+// Montgomery product (CIOS), fully unrolled so that the compiler keeps the accumulator in registers and, where the field
+// is a compile-time constant at the call site (HFR / HFP), folds the modulus into immediates
 inline Fe4 mul(const Field& F, const Fe4& a, const Fe4& b) {
-  uint64_t t[6] = {0, 0, 0, 0, 0, 0};
-  for (int i = 0; i < 4; i++) {
-    u128 c = 0;
-    for (int j = 0; j < 4; j++) {
-      c += (u128)a.l[j] * b.l[i] + t[j];
-      t[j] = (uint64_t)c;
-      c >>= 64;
-    }
-    c += t[4];
-    t[4] = (uint64_t)c;
-    t[5] = (uint64_t)(c >> 64);
-    uint64_t q = t[0] * F.ninv;
-    c = (u128)q * F.m[0] + t[0];
-    c >>= 64;
-    for (int j = 1; j < 4; j++) {
-      c += (u128)q * F.m[j] + t[j];
-      t[j - 1] = (uint64_t)c;
-      c >>= 64;
-    }
-    c += t[4];
-    t[3] = (uint64_t)c;
-    t[4] = t[5] + (uint64_t)(c >> 64);
+  uint64_t t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+  const uint64_t m0 = F.m[0], m1 = F.m[1], m2 = F.m[2], m3 = F.m[3], ninv = F.ninv;
+  const uint64_t a0 = a.l[0], a1 = a.l[1], a2 = a.l[2], a3 = a.l[3];
+#define B200ZK_CIOS_STEP(bi)                                   \
+  {                                                            \
+    u128 c = (u128)a0 * (bi) + t0;                             \
+    t0 = (uint64_t)c;                                          \
+    c = (c >> 64) + (u128)a1 * (bi) + t1;                      \
+    t1 = (uint64_t)c;                                          \
+    c = (c >> 64) + (u128)a2 * (bi) + t2;                      \
+    t2 = (uint64_t)c;                                          \
+    c = (c >> 64) + (u128)a3 * (bi) + t3;                      \
+    t3 = (uint64_t)c;                                          \
+    c = (c >> 64) + t4;                                        \
+    t4 = (uint64_t)c;                                          \
+    const uint64_t t5 = (uint64_t)(c >> 64);                   \
+    const uint64_t q = t0 * ninv;                              \
+    c = ((u128)q * m0 + t0) >> 64;                             \
+    c += (u128)q * m1 + t1;                                    \
+    t0 = (uint64_t)c;                                          \
+    c = (c >> 64) + (u128)q * m2 + t2;                         \
+    t1 = (uint64_t)c;                                          \
+    c = (c >> 64) + (u128)q * m3 + t3;                         \
+    t2 = (uint64_t)c;                                          \
+    c = (c >> 64) + t4;                                        \
+    t3 = (uint64_t)c;                                          \
+    t4 = t5 + (uint64_t)(c >> 64);                             \
   }
+  B200ZK_CIOS_STEP(b.l[0])
+  B200ZK_CIOS_STEP(b.l[1])
+  B200ZK_CIOS_STEP(b.l[2])
+  B200ZK_CIOS_STEP(b.l[3])
+#undef B200ZK_CIOS_STEP
+  uint64_t t[4] = {t0, t1, t2, t3};
+  if (t4 || geq(t, F.m)) raw_sub(t, t, F.m);
   Fe4 r;
-  if (t[4] || geq(t, F.m)) raw_sub(t, t, F.m);
   memcpy(r.l, t, 32);
   return r;
 }
@@ -130,16 +143,62 @@ inline Fe4 pow_u64(const Field& F, Fe4 base, uint64_t e) {
   }
   return acc;
 }
+// a^-1 (Montgomery in, Montgomery out; inv(0) = 0 like gnark's Inverse): binary extended Euclid on the stored
+// integer aR, which yields a^-1 R^-1, brought back to Montgomery form by one multiplication by R^3.
 inline Fe4 inv(const Field& F, const Fe4& a) {
-  uint64_t e[4];
-  memcpy(e, F.m, 32);
-  e[0] -= 2;
-  Fe4 acc = F.one, base = a;
-  for (int i = 0; i < 256; i++) {
-    if ((e[i / 64] >> (i % 64)) & 1) acc = mul(F, acc, base);
-    base = mul(F, base, base);
+  if (is_zero(a)) return a;
+  auto is_one = [](const uint64_t* x) { return x[0] == 1 && (x[1] | x[2] | x[3]) == 0; };
+  auto shr1 = [](uint64_t* x, uint64_t top) {
+    x[0] = (x[0] >> 1) | (x[1] << 63);
+    x[1] = (x[1] >> 1) | (x[2] << 63);
+    x[2] = (x[2] >> 1) | (x[3] << 63);
+    x[3] = (x[3] >> 1) | (top << 63);
+  };
+  auto halve_mod = [&](uint64_t* x) {  // x / 2 mod m
+    uint64_t top = 0;
+    if (x[0] & 1) {
+      u128 c = 0;
+      for (int i = 0; i < 4; i++) {
+        c += (u128)x[i] + F.m[i];
+        x[i] = (uint64_t)c;
+        c >>= 64;
+      }
+      top = (uint64_t)c;
+    }
+    shr1(x, top);
+  };
+  auto sub_mod = [&](uint64_t* x, const uint64_t* y) {  // x - y mod m, both < m
+    if (geq(x, y)) {
+      raw_sub(x, x, y);
+    } else {
+      uint64_t t[4];
+      raw_sub(t, y, x);
+      raw_sub(x, F.m, t);
+    }
+  };
+  uint64_t u[4], v[4], x1[4] = {1, 0, 0, 0}, x2[4] = {0, 0, 0, 0};
+  memcpy(u, a.l, 32);
+  memcpy(v, F.m, 32);
+  while (!is_one(u) && !is_one(v)) {
+    while (!(u[0] & 1)) {
+      shr1(u, 0);
+      halve_mod(x1);
+    }
+    while (!(v[0] & 1)) {
+      shr1(v, 0);
+      halve_mod(x2);
+    }
+    if (geq(u, v)) {
+      raw_sub(u, u, v);
+      sub_mod(x1, x2);
+    } else {
+      raw_sub(v, v, u);
+      sub_mod(x2, x1);
+    }
   }
-  return acc;
+  Fe4 r;
+  memcpy(r.l, is_one(u) ? x1 : x2, 32);
+  return mul(F, r, mul(F, F.r2, F.r2));
 }
 
 // fr.Element.Marshal(): 32-byte big-endian regular form
