@@ -80,6 +80,8 @@ struct State {
     std::map<size_t, std::shared_ptr<struct Keyed>> by_nvalues;
   };
   std::list<Entry> circuits;
+  // at process exit the CUDA runtime may already be gone: leave the device allocations to the driver
+  ~State() { ctx = nullptr; }
 };
 struct Keyed {  // everything that depends on (circuit, number of values) only
   WirePlan plan;
