@@ -343,6 +343,12 @@ int b200zk_msm_g1(b200zk_ctx* ctx, const b200zk_bases* bases, const void* scalar
   return B200ZK_OK;
 }
 
+int b200zk_msm_set_reduce_chunk(b200zk_ctx* ctx, int chunk_log) {
+  if (!ctx || (chunk_log != 0 && chunk_log != 3 && chunk_log != 5)) return B200ZK_ERR_BAD_ARG;
+  ctx->msm_chunk_log = chunk_log;
+  return B200ZK_OK;
+}
+
 int b200zk_msm_set_small_path(b200zk_ctx* ctx, int on) {
   if (!ctx) return B200ZK_ERR_BAD_ARG;
   ctx->msm_no_tiny = on ? 0 : 1;

@@ -25,8 +25,9 @@
 
 namespace b200zk {
 
-static constexpr int CHUNK_LOG = 5;
-static constexpr int CHUNK = 1 << CHUNK_LOG;   // buckets per running-sum chunk
+static constexpr int CHUNK_LOG = 5;            // buckets per running-sum chunk: 2^5 when the reduction is throughput-bound,
+static constexpr int CHUNK = 1 << CHUNK_LOG;   // 2^3 for small bucket counts, where the chunk's chain of additions is the latency
+static constexpr int CHUNK_LOG_SMALL = 3;
 static constexpr int BIG_CHUNK = 8192;         // sorted entries per CTA in the long-run path
 static constexpr int BIG_THREADS = 256;
 static constexpr size_t TINY_MAX_TERMS = (size_t)1 << 17;  // (points x windows) up to which the bucket pipeline is skipped
@@ -407,13 +408,14 @@ __global__ void __launch_bounds__(BIG_THREADS) msm_big_reduce_kernel(const unsig
 //    R3: one CTA per set: warp p finishes plane p (lane partial sums + warp-shuffle tree), then
 //        S = P_0 + 32 * sum_k 2^k P_{1+k}  by doublings
 // ---------------------------------------------------------------------------------------------------
+template <int CL>
 __global__ void __launch_bounds__(128) msm_reduce_r1_kernel(const void* __restrict__ buckets, unsigned nchunks_total,
                                                             void* __restrict__ run, void* __restrict__ acc_out) {
   unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nchunks_total) return;
   G1XYZZ r = g1_xyzz_inf(), a = g1_xyzz_inf();
-  for (int j = CHUNK - 1; j >= 0; j--) {
-    G1XYZZ q = g1_load_xyzz(buckets, (size_t)t * CHUNK + j);
+  for (int j = (1 << CL) - 1; j >= 0; j--) {
+    G1XYZZ q = g1_load_xyzz(buckets, ((size_t)t << CL) + j);
     g1_add(r, q);
     g1_add(a, r);
   }
@@ -447,7 +449,7 @@ __global__ void __launch_bounds__(BIG_THREADS) msm_reduce_r2_kernel(const void* 
 
 // grid = sets, block = 8 warps; warp w finishes planes w, w+8, ...
 __global__ void __launch_bounds__(256) msm_reduce_r3_kernel(const void* __restrict__ partial, unsigned nplanes,
-                                                            unsigned nslices, void* __restrict__ set_sums) {
+                                                            unsigned nslices, unsigned chunk_log, void* __restrict__ set_sums) {
   __shared__ G1XYZZ plane_sum[MAX_PLANES];
   const unsigned set = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (unsigned plane = warp; plane < nplanes; plane += 8) {
@@ -466,7 +468,7 @@ __global__ void __launch_bounds__(256) msm_reduce_r3_kernel(const void* __restri
       g1_double(s);
       g1_add(s, plane_sum[k]);
     }
-    for (int k = 0; k < CHUNK_LOG; k++) g1_double(s);
+    for (unsigned k = 0; k < chunk_log; k++) g1_double(s);
     g1_add(s, plane_sum[0]);
     g1_store_xyzz(set_sums, set, s);
   }
@@ -765,7 +767,10 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
     size_t bl = 4 * avg + 256;
     sh.big_len = (unsigned)(bl > 0x7fffffff ? 0x7fffffff : bl);
   }
-  const unsigned chunks_per_set = sh.B / CHUNK;
+  // short chunks while the bucket count is small enough for the bit-plane sums to stay cheap
+  const unsigned chunk_log = (ctx->msm_chunk_log ? (unsigned)ctx->msm_chunk_log
+                                                 : ((size_t)nbuckets <= ((size_t)1 << 17) ? CHUNK_LOG_SMALL : CHUNK_LOG));
+  const unsigned chunks_per_set = sh.B >> chunk_log;
   unsigned chunk_bits = 0;
   while ((1u << chunk_bits) < chunks_per_set) chunk_bits++;
   const unsigned nplanes = 1 + chunk_bits;
@@ -890,13 +895,16 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
   {
     PhaseTimer pt(ctx, PH_MSM_REDUCE);
     const unsigned tot1 = sh.nsets * chunks_per_set;
-    msm_reduce_r1_kernel<<<(tot1 + 127) / 128, 128, 0, st>>>(ctx->msm_buckets.p, tot1, run, acc);
+    if (chunk_log == CHUNK_LOG_SMALL)
+      msm_reduce_r1_kernel<CHUNK_LOG_SMALL><<<(tot1 + 127) / 128, 128, 0, st>>>(ctx->msm_buckets.p, tot1, run, acc);
+    else
+      msm_reduce_r1_kernel<CHUNK_LOG><<<(tot1 + 127) / 128, 128, 0, st>>>(ctx->msm_buckets.p, tot1, run, acc);
     B200ZK_LAUNCH_CHECK(ctx, "msm_reduce_r1_kernel");
     const size_t shm = BIG_THREADS * sizeof(G1XYZZ);
     dim3 grid2(nslices, nplanes, sh.nsets);
     msm_reduce_r2_kernel<<<grid2, BIG_THREADS, shm, st>>>(run, acc, chunks_per_set, nslices, partial);
     B200ZK_LAUNCH_CHECK(ctx, "msm_reduce_r2_kernel");
-    msm_reduce_r3_kernel<<<sh.nsets, 256, 0, st>>>(partial, nplanes, nslices, set_sums);
+    msm_reduce_r3_kernel<<<sh.nsets, 256, 0, st>>>(partial, nplanes, nslices, chunk_log, set_sums);
     B200ZK_LAUNCH_CHECK(ctx, "msm_reduce_r3_kernel");
   }
   {

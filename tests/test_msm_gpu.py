@@ -388,3 +388,25 @@ def test_small_msm_path_with_window_table(ctx, n):
     finally:
         lib.b200zk_msm_set_small_path(ctx.handle, 1)
         srs.close()
+
+
+@pytest.mark.parametrize("log2n", [13, 17])
+def test_bucket_reduction_chunk_sizes_agree(ctx, log2n):
+    """the bucket reduction with 8-bucket and 32-bucket running-sum chunks (latency- vs throughput-oriented), classic
+    windows and window table, against the oracle"""
+    lib = zk.load()
+    n = (1 << log2n) + 5
+    pts = structured(n)
+    sc = cref.random_fr(n, 0xB2000001 + 31 + log2n)
+    want = cref.msm(pts, sc, n, nthreads=cref.ncores())
+    srs = zk.SRS(pts, ctx)
+    try:
+        for table in (False, True):
+            if table:
+                srs.precompute()
+            for cl in (3, 5, 0):
+                lib.b200zk_msm_set_reduce_chunk(ctx.handle, cl)
+                assert zk.MultiExp(srs, sc) == want, (table, cl)
+    finally:
+        lib.b200zk_msm_set_reduce_chunk(ctx.handle, 0)
+        srs.close()
