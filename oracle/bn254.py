@@ -255,6 +255,30 @@ def g1_structured_bases(n: int, a: int, b: int) -> List[Affine]:
     return out
 
 
+def g1_pseudo_random_points(n: int, seed: int) -> List[Affine]:
+    """Bases with no known discrete-log relation (bases (ii)): x from a SplitMix64 stream, incremented until
+    x^3 + 3 is a square; y = (x^3 + 3)^((p+1)/4) (p = 3 mod 4), the smaller root when the stream says so."""
+    out = []
+    state = seed & MASK64
+    for _ in range(n):
+        x = 0
+        for _k in range(4):
+            state, z = splitmix64(state)
+            x = (x << 64) | z
+        x %= P_MOD
+        while True:
+            rhs = (x * x * x + 3) % P_MOD
+            y = pow(rhs, (P_MOD + 1) // 4, P_MOD)
+            if y * y % P_MOD == rhs:
+                break
+            x = (x + 1) % P_MOD
+        state, z = splitmix64(state)
+        if z & 1:
+            y = P_MOD - y
+        out.append((x, y))
+    return out
+
+
 # --------------------------------------------------------------------------------------------------
 # NTT with gnark fft.Domain semantics
 # --------------------------------------------------------------------------------------------------

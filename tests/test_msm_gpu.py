@@ -410,3 +410,27 @@ def test_bucket_reduction_chunk_sizes_agree(ctx, log2n):
     finally:
         lib.b200zk_msm_set_reduce_chunk(ctx.handle, 0)
         srs.close()
+
+
+def test_pseudo_random_bases(ctx):
+    """SURVEY.md §8d bases (ii): points by try-and-increment (no structure between the bases), seed 0xB2000002, against
+    the C oracle — uniform and witness-like scalars, classic windows and window table."""
+    n = 1 << 13
+    pts = np.frombuffer(o.g1_to_bytes(o.g1_pseudo_random_points(n, 0xB2000002)), dtype=np.uint8)
+    uniform = cref.random_fr(n, 0xB2000001)
+    vals = o.random_fr(n, 0xB2000001 + 1)
+    for i in range(n):
+        if i % 4 < 2:
+            vals[i] = 0
+        elif i % 4 == 2:
+            vals[i] &= 0xFFFF
+    witness_like = np.frombuffer(o.fr_to_mont_bytes(vals), dtype=np.uint8)
+    srs = zk.SRS(pts, ctx)
+    try:
+        for table in (False, True):
+            if table:
+                srs.precompute()
+            for sc in (uniform, witness_like):
+                assert zk.MultiExp(srs, sc) == cref.msm(pts, sc, n, nthreads=cref.ncores())
+    finally:
+        srs.close()

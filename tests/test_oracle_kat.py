@@ -143,3 +143,13 @@ def test_signed_digit_top_window_never_carries():
         W = (255 + c - 1) // c
         top = (o.R_MOD - 1) >> (c * (W - 1))
         assert top + 1 < (1 << (c - 1)), c
+
+
+def test_pseudo_random_bases_are_on_the_curve_and_in_the_group():
+    from oracle import bn254 as o
+
+    pts = o.g1_pseudo_random_points(20, 0xB2000002)
+    assert len(set(pts)) == 20
+    for x, y in pts:
+        assert (y * y - x * x * x - 3) % o.P_MOD == 0
+    assert o.g1_mul(pts[0], o.R_MOD) is None            # cofactor 1: every curve point has order r
