@@ -201,6 +201,10 @@ int b200zk_plonk_pk_poly(b200zk_ctx* ctx, const b200zk_plonk_pk* pk, int which, 
 int b200zk_plonk_prove(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solution_host, const void* blinding_host,
                        void* proof_out);
 long long b200zk_plonk_unsatisfied_row(const b200zk_plonk_pk* pk);
+/* tests / tuning: the independent commitments of one prover round (L,R,O; H1,H2,H3; the 8 of Setup) run on 3 MSM lanes
+ * of the context (own stream and workspace each) so that the latency-bound phases of one MSM hide under the bucket
+ * accumulation of another; 1 = one after the other.  Results do not depend on it. */
+int b200zk_plonk_set_commit_lanes(b200zk_ctx* ctx, int lanes);
 /* The same prover fed with what PlonkProveWithPK receives (/root/reference/gnark_backend_ffi/main.go:24-37): the hex text of
  * the value vector, 64 characters per element (32 bytes big-endian, regular form), WITHOUT the 8-character count prefix.
  * DeserializeFelts (fr.SetBytes: reduce, Montgomery form) and BuildWitnesses (values -> publics then secrets) run on the

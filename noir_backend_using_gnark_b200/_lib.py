@@ -97,6 +97,7 @@ def load() -> C.CDLL:
         "b200zk_plonk_pk_poly": (i, [vp, vp, i, vp]),
         "b200zk_plonk_prove": (i, [vp, vp, vp, vp, vp]),
         "b200zk_plonk_unsatisfied_row": (C.c_longlong, [vp]),
+        "b200zk_plonk_set_commit_lanes": (i, [vp, i]),
         "b200zk_plonk_set_solution_map": (i, [vp, vp, vp, sz]),
         "b200zk_plonk_prove_hex": (i, [vp, vp, vp, sz, vp, vp]),
         "b200zk_microbench": (i, [vp, i, C.POINTER(C.c_double)]),

@@ -64,6 +64,15 @@ int b200zk_init(int device, b200zk_ctx** out) {
       delete ctx;
       return B200ZK_ERR_CUDA;
     }
+  ctx->ws[0].stream = ctx->stream;
+  for (int l = 0; l < MSM_LANES; l++) {
+    if ((l > 0 && cudaStreamCreateWithFlags(&ctx->ws[l].stream, cudaStreamNonBlocking) != cudaSuccess) ||
+        cudaEventCreateWithFlags(&ctx->ws[l].done, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      delete ctx;
+      return B200ZK_ERR_CUDA;
+    }
+  }
   *out = ctx;
   return B200ZK_OK;
 }
@@ -74,17 +83,14 @@ void b200zk_destroy(b200zk_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   ntt_free_domains(ctx);
   free_buf(ctx->stage);
-  free_buf(ctx->msm_digits);
-  free_buf(ctx->msm_sorted);
-  free_buf(ctx->msm_counts);
-  free_buf(ctx->msm_starts);
-  free_buf(ctx->msm_cursor);
-  free_buf(ctx->msm_buckets);
-  free_buf(ctx->msm_tmp);
-  free_buf(ctx->msm_small);
-  free_buf(ctx->msm_scan_tmp);
-  free_buf(ctx->msm_big);
-  free_buf(ctx->msm_part);
+  for (int l = 0; l < MSM_LANES; l++) {
+    MsmWorkspace& w = ctx->ws[l];
+    DeviceBuf* bufs[] = {&w.msm_digits, &w.msm_sorted, &w.msm_counts, &w.msm_starts, &w.msm_cursor, &w.msm_buckets,
+                         &w.msm_tmp, &w.msm_small, &w.msm_scan_tmp, &w.msm_big, &w.msm_part};
+    for (auto bp : bufs) free_buf(*bp);
+    if (l > 0 && w.stream) cudaStreamDestroy(w.stream);
+    if (w.done) cudaEventDestroy(w.done);
+  }
   cudaStreamDestroy(ctx->stream);
   if (ctx->side) cudaStreamDestroy(ctx->side);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -340,6 +346,12 @@ int b200zk_msm_g1(b200zk_ctx* ctx, const b200zk_bases* bases, const void* scalar
   }
   B200ZK_CUDA(ctx, cudaMemcpyAsync(out_affine_host, stage, 64, cudaMemcpyDeviceToHost, ctx->stream));
   B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200ZK_OK;
+}
+
+int b200zk_plonk_set_commit_lanes(b200zk_ctx* ctx, int lanes) {
+  if (!ctx || (lanes != 1 && lanes != MSM_LANES)) return B200ZK_ERR_BAD_ARG;
+  ctx->msm_single_lane = lanes == 1;
   return B200ZK_OK;
 }
 

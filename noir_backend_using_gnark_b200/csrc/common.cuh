@@ -40,6 +40,19 @@ struct DeviceBuf {
 
 }  // namespace b200zk
 
+namespace b200zk {
+// MSM workspace (grown on demand, reused across calls).  A context owns MSM_LANES of them, each with its own stream, so
+// that independent MSMs (the three commitments of one prover round) can be in flight together: the latency-bound front
+// and back ends of one hide under the bucket accumulation of another.
+static constexpr int MSM_LANES = 3;
+struct MsmWorkspace {
+  DeviceBuf msm_digits, msm_sorted, msm_counts, msm_starts, msm_cursor, msm_buckets, msm_tmp, msm_small, msm_scan_tmp,
+      msm_big, msm_part;
+  cudaStream_t stream = nullptr;   // lane 0: the context stream
+  cudaEvent_t done = nullptr;      // recorded after the lane's last MSM (lanes > 0)
+};
+}  // namespace b200zk
+
 struct b200zk_bases {
   const void* dev = nullptr;  // n x 64 B affine points
   size_t n = 0;
@@ -59,6 +72,7 @@ struct b200zk_ctx {
   cudaEvent_t ev_chunk[8] = {};  // host-scalar MSM: chunk i of the scalars has landed (copy stream -> compute stream)
   int msm_host_chunks = 0;       // 0 = choose from n; 1 = never split (tests / tuning)
   int msm_chunk_log = 0;         // tests / tuning: force the running-sum chunk size of the bucket reduction (3 or 5)
+  int msm_single_lane = 0;       // tests / tuning: the prover's commitment rounds run one MSM after the other
   int msm_no_tiny = 0;           // tests: force the bucket pipeline also for small table-mode MSMs
   uint64_t launches = 0;
   char cuda_err[256] = {0};
@@ -70,9 +84,7 @@ struct b200zk_ctx {
   b200zk::NttDomain domains[B200ZK_MAX_LOG2N + 1];
   // staging buffer for host-pointer entry points
   b200zk::DeviceBuf stage;
-  // MSM workspace (grown on demand, reused across calls)
-  b200zk::DeviceBuf msm_digits, msm_sorted, msm_counts, msm_starts, msm_cursor, msm_buckets, msm_tmp, msm_small,
-      msm_scan_tmp, msm_big, msm_part;
+  b200zk::MsmWorkspace ws[b200zk::MSM_LANES];
 };
 
 namespace b200zk {
@@ -102,11 +114,11 @@ inline int set_cuda_error(b200zk_ctx* ctx, cudaError_t e, const char* where) {
     if (rc__ != B200ZK_OK) return rc__; \
   } while (0)
 
-inline int ensure(b200zk_ctx* ctx, DeviceBuf& b, size_t bytes) {
+inline int ensure(b200zk_ctx* ctx, DeviceBuf& b, size_t bytes, cudaStream_t user = nullptr) {
   if (b.cap >= bytes) return B200ZK_OK;
   if (b.p) {
     // the buffer may still be in use by work enqueued earlier on the stream
-    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    B200ZK_CUDA(ctx, cudaStreamSynchronize(user ? user : ctx->stream));
     B200ZK_CUDA(ctx, cudaFree(b.p));
     b.p = nullptr;
     b.cap = 0;
@@ -131,7 +143,8 @@ struct PhaseTimer {
   b200zk_ctx* ctx;
   PhaseRecord rec;
   bool on;
-  PhaseTimer(b200zk_ctx* c, int phase) : ctx(c), on(c->profiling) {
+  cudaStream_t st;
+  PhaseTimer(b200zk_ctx* c, int phase, cudaStream_t stream = nullptr) : ctx(c), on(c->profiling), st(stream ? stream : c->stream) {
     if (!on) return;
     rec.phase = phase;
     if (cudaEventCreate(&rec.e0) != cudaSuccess || cudaEventCreate(&rec.e1) != cudaSuccess) {
@@ -139,11 +152,11 @@ struct PhaseTimer {
       cudaGetLastError();
       return;
     }
-    cudaEventRecord(rec.e0, ctx->stream);
+    cudaEventRecord(rec.e0, st);
   }
   ~PhaseTimer() {
     if (!on) return;
-    cudaEventRecord(rec.e1, ctx->stream);
+    cudaEventRecord(rec.e1, st);
     ctx->records.push_back(rec);
   }
 };
@@ -155,8 +168,9 @@ int ntt_dist_run(b200zk_ctx* ctx, const void* src, void* dst, unsigned log2n, un
 int bit_reverse_run(b200zk_ctx* ctx, void* a_dev, unsigned log2n);
 void ntt_free_domains(b200zk_ctx* ctx);
 int ntt_prepare(b200zk_ctx* ctx, unsigned log2n);  // builds the twiddle / coset tables of a domain if missing
+// lane: which workspace / stream of the context runs it (0 = the context stream)
 int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const void* scalars_dev, size_t n,
-            void* out_dev, int out_kind);
+            void* out_dev, int out_kind, int lane = 0);
 int msm_precompute_run(b200zk_ctx* ctx, b200zk_bases* bases, int c);
 unsigned msm_window_count(const b200zk_ctx* ctx, const b200zk_bases* bases, size_t n);
 int g1_sum_run(b200zk_ctx* ctx, const void* partials_dev, size_t count, void* out_affine_dev);

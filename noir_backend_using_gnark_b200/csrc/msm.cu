@@ -708,11 +708,12 @@ unsigned msm_window_count(const b200zk_ctx* ctx, const b200zk_bases* bases, size
 }
 
 int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const void* scalars_dev, size_t n,
-            void* out_dev, int out_kind) {
-  if (!bases || !out_dev || (n && !scalars_dev)) return B200ZK_ERR_BAD_ARG;
+            void* out_dev, int out_kind, int lane) {
+  if (!bases || !out_dev || (n && !scalars_dev) || lane < 0 || lane >= MSM_LANES) return B200ZK_ERR_BAD_ARG;
+  MsmWorkspace& ws = ctx->ws[lane];
   if (first_base > bases->n || n > bases->n - first_base) return B200ZK_ERR_BAD_ARG;
   if (n >= ((size_t)1 << 31)) return B200ZK_ERR_UNSUPPORTED;
-  cudaStream_t st = ctx->stream;
+  cudaStream_t st = ws.stream;
   if (n == 0) {
     // empty sum = point at infinity: affine (0,0) / XYZZ with ZZ = 0
     B200ZK_CUDA(ctx, cudaMemsetAsync(out_dev, 0, out_kind == 0 ? 64 : 128, st));
@@ -729,12 +730,12 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
     memcpy(sh.wstart, bases->tab_wstart, sizeof(sh.wstart));
     const unsigned terms = (unsigned)(n * sh.W);
     const unsigned blocks = (terms + BIG_THREADS - 1) / BIG_THREADS;
-    B200ZK_TRY(ensure(ctx, ctx->msm_big, (size_t)blocks * 128));
+    B200ZK_TRY(ensure(ctx, ws.msm_big, (size_t)blocks * 128, st));
     const size_t shm = (size_t)BIG_THREADS * sizeof(G1XYZZ);
-    PhaseTimer pt(ctx, PH_MSM_ACCUMULATE);
-    msm_tiny_kernel<<<blocks, BIG_THREADS, shm, st>>>(bases->table, (const uint4*)scalars_dev, (unsigned)n, sh, ctx->msm_big.p);
+    PhaseTimer pt(ctx, PH_MSM_ACCUMULATE, st);
+    msm_tiny_kernel<<<blocks, BIG_THREADS, shm, st>>>(bases->table, (const uint4*)scalars_dev, (unsigned)n, sh, ws.msm_big.p);
     B200ZK_LAUNCH_CHECK(ctx, "msm_tiny_kernel");
-    msm_tiny_final_kernel<<<1, BIG_THREADS, shm, st>>>(ctx->msm_big.p, blocks, out_dev, out_kind);
+    msm_tiny_final_kernel<<<1, BIG_THREADS, shm, st>>>(ws.msm_big.p, blocks, out_dev, out_kind);
     B200ZK_LAUNCH_CHECK(ctx, "msm_tiny_final_kernel");
     return B200ZK_OK;
   }
@@ -781,39 +782,39 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
   const unsigned big_cap = nbuckets / 4 + 16;
   const size_t max_big_chunks = total / BIG_CHUNK + big_cap + 1;
 
-  B200ZK_TRY(ensure(ctx, ctx->msm_sorted, total * sizeof(unsigned)));
-  B200ZK_TRY(ensure(ctx, ctx->msm_counts, (size_t)(nbuckets + 1) * 4));
-  B200ZK_TRY(ensure(ctx, ctx->msm_starts, (size_t)(nbuckets + 1) * 4));
-  B200ZK_TRY(ensure(ctx, ctx->msm_cursor, (size_t)(nbuckets + 1) * 4));
-  B200ZK_TRY(ensure(ctx, ctx->msm_buckets, (size_t)nbuckets * 128));
-  B200ZK_TRY(ensure(ctx, ctx->msm_tmp,
+  B200ZK_TRY(ensure(ctx, ws.msm_sorted, total * sizeof(unsigned), st));
+  B200ZK_TRY(ensure(ctx, ws.msm_counts, (size_t)(nbuckets + 1) * 4, st));
+  B200ZK_TRY(ensure(ctx, ws.msm_starts, (size_t)(nbuckets + 1) * 4, st));
+  B200ZK_TRY(ensure(ctx, ws.msm_cursor, (size_t)(nbuckets + 1) * 4, st));
+  B200ZK_TRY(ensure(ctx, ws.msm_buckets, (size_t)nbuckets * 128, st));
+  B200ZK_TRY(ensure(ctx, ws.msm_tmp,
                     ((size_t)sh.nsets * chunks_per_set * 2 + (size_t)sh.nsets * nplanes * nslices + sh.nsets) * 128));
-  B200ZK_TRY(ensure(ctx, ctx->msm_small, sizeof(BigPlan) + (size_t)big_cap * 8 + max_big_chunks * 8));
-  B200ZK_TRY(ensure(ctx, ctx->msm_big, max_big_chunks * 128));
+  B200ZK_TRY(ensure(ctx, ws.msm_small, sizeof(BigPlan) + (size_t)big_cap * 8 + max_big_chunks * 8, st));
+  B200ZK_TRY(ensure(ctx, ws.msm_big, max_big_chunks * 128, st));
   size_t scan_bytes = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (unsigned*)nullptr, (unsigned*)nullptr, (int)(nbuckets + 1), st);
   size_t sort_bytes = 0;
   cub::DeviceRadixSort::SortPairsDescending(nullptr, sort_bytes, (const unsigned*)nullptr, (unsigned*)nullptr,
                                             (const unsigned*)nullptr, (unsigned*)nullptr, (int)nbuckets, 0, 32, st);
   if (sort_bytes > scan_bytes) scan_bytes = sort_bytes;
-  B200ZK_TRY(ensure(ctx, ctx->msm_scan_tmp, scan_bytes));
+  B200ZK_TRY(ensure(ctx, ws.msm_scan_tmp, scan_bytes, st));
   // run-length ordering scratch: [iota | sorted lengths (unused) | order]
-  B200ZK_TRY(ensure(ctx, ctx->msm_digits, (size_t)nbuckets * 12));
-  unsigned* iota = (unsigned*)ctx->msm_digits.p;
+  B200ZK_TRY(ensure(ctx, ws.msm_digits, (size_t)nbuckets * 12, st));
+  unsigned* iota = (unsigned*)ws.msm_digits.p;
   unsigned* len_sorted = iota + nbuckets;
   unsigned* order = len_sorted + nbuckets;
 
-  unsigned* sorted = (unsigned*)ctx->msm_sorted.p;
-  unsigned* counts = (unsigned*)ctx->msm_counts.p;
-  unsigned* starts = (unsigned*)ctx->msm_starts.p;
-  unsigned* cursor = (unsigned*)ctx->msm_cursor.p;
-  char* tmp = (char*)ctx->msm_tmp.p;
+  unsigned* sorted = (unsigned*)ws.msm_sorted.p;
+  unsigned* counts = (unsigned*)ws.msm_counts.p;
+  unsigned* starts = (unsigned*)ws.msm_starts.p;
+  unsigned* cursor = (unsigned*)ws.msm_cursor.p;
+  char* tmp = (char*)ws.msm_tmp.p;
   void* run = tmp;
   void* acc = tmp + (size_t)sh.nsets * chunks_per_set * 128;
   void* partial = tmp + (size_t)sh.nsets * chunks_per_set * 256;
   void* set_sums = (char*)partial + (size_t)sh.nsets * nplanes * nslices * 128;
-  BigPlan* plan = (BigPlan*)ctx->msm_small.p;
-  unsigned* big_bucket = (unsigned*)((char*)ctx->msm_small.p + sizeof(BigPlan));
+  BigPlan* plan = (BigPlan*)ws.msm_small.p;
+  unsigned* big_bucket = (unsigned*)((char*)ws.msm_small.p + sizeof(BigPlan));
   unsigned* big_first = big_bucket + big_cap;
   unsigned* chunk_bucket = big_first + big_cap;
   unsigned* chunk_idx = chunk_bucket + max_big_chunks;
@@ -821,28 +822,28 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
   B200ZK_CUDA(ctx, cudaMemsetAsync(counts, 0, (size_t)(nbuckets + 1) * 4, st));
   B200ZK_CUDA(ctx, cudaMemsetAsync(plan, 0, sizeof(BigPlan), st));
   {
-    PhaseTimer pt(ctx, PH_MSM_DIGITS);
+    PhaseTimer pt(ctx, PH_MSM_DIGITS, st);
     unsigned blocks = (unsigned)((n + 255) / 256);
     msm_hist_kernel<<<blocks, 256, 0, st>>>((const uint4*)scalars_dev, n, sh, counts);
     B200ZK_LAUNCH_CHECK(ctx, "msm_hist_kernel");
   }
   {
-    PhaseTimer pt(ctx, PH_MSM_SCAN);
-    B200ZK_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->msm_scan_tmp.p, scan_bytes, counts, starts, (int)(nbuckets + 1), st));
+    PhaseTimer pt(ctx, PH_MSM_SCAN, st);
+    B200ZK_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ws.msm_scan_tmp.p, scan_bytes, counts, starts, (int)(nbuckets + 1), st));
     ctx->launches++;
     unsigned blocks = (nbuckets + 1 + 255) / 256;
     copy_u32_kernel<<<blocks, 256, 0, st>>>(starts, cursor, nbuckets + 1);
     B200ZK_LAUNCH_CHECK(ctx, "copy_u32_kernel");
     iota_u32_kernel<<<blocks, 256, 0, st>>>(iota, nbuckets);
     B200ZK_LAUNCH_CHECK(ctx, "iota_u32_kernel");
-    size_t sb = ctx->msm_scan_tmp.cap;
-    B200ZK_CUDA(ctx, cub::DeviceRadixSort::SortPairsDescending(ctx->msm_scan_tmp.p, sb, (const unsigned*)counts, len_sorted,
+    size_t sb = ws.msm_scan_tmp.cap;
+    B200ZK_CUDA(ctx, cub::DeviceRadixSort::SortPairsDescending(ws.msm_scan_tmp.p, sb, (const unsigned*)counts, len_sorted,
                                                                (const unsigned*)iota, order, (int)nbuckets, 0, 32, st));
     ctx->launches += 4;
   }
   if (total >= ((size_t)1 << 18) && ctx->msm_flat_scatter == 2) {
     // two-level scatter (large problems): partition, then shared-memory counting sort per partition
-    PhaseTimer pt(ctx, PH_MSM_SCATTER);
+    PhaseTimer pt(ctx, PH_MSM_SCATTER, st);
     unsigned lgb = 0;
     while ((1u << lgb) < nbuckets) lgb++;
     unsigned part_log = lgb > 7 ? lgb - 7 : 0;
@@ -850,9 +851,9 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
     if (part_log < 8) part_log = 8;
     while (((nbuckets + (1u << part_log) - 1) >> part_log) > (unsigned)MAX_PARTS) part_log++;
     const unsigned nparts = (nbuckets + (1u << part_log) - 1) >> part_log;
-    B200ZK_TRY(ensure(ctx, ctx->msm_part, total * sizeof(uint2) + (size_t)MAX_PARTS * 4));
-    uint2* tmp2 = (uint2*)ctx->msm_part.p;
-    unsigned* part_cursor = (unsigned*)((char*)ctx->msm_part.p + total * sizeof(uint2));
+    B200ZK_TRY(ensure(ctx, ws.msm_part, total * sizeof(uint2) + (size_t)MAX_PARTS * 4, st));
+    uint2* tmp2 = (uint2*)ws.msm_part.p;
+    unsigned* part_cursor = (unsigned*)((char*)ws.msm_part.p + total * sizeof(uint2));
     // partition p owns sorted[starts[p << part_log] ...): its cursor starts there
     copy_strided_u32_kernel<<<(nparts + 255) / 256, 256, 0, st>>>(starts, part_cursor, nparts, part_log);
     B200ZK_LAUNCH_CHECK(ctx, "copy_strided_u32_kernel");
@@ -865,7 +866,7 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
     msm_scatter_local_kernel<<<nparts, 1024, shm, st>>>(tmp2, starts, part_log, nbuckets, sorted);
     B200ZK_LAUNCH_CHECK(ctx, "msm_scatter_local_kernel");
   } else {
-    PhaseTimer pt(ctx, PH_MSM_SCATTER);
+    PhaseTimer pt(ctx, PH_MSM_SCATTER, st);
     unsigned blocks = (unsigned)((n + 255) / 256);
     if (sh.W <= 13)
       msm_scatter_kernel<13><<<blocks, 256, 0, st>>>((const uint4*)scalars_dev, n, sh, cursor, sorted);
@@ -876,32 +877,32 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
     B200ZK_LAUNCH_CHECK(ctx, "msm_scatter_kernel");
   }
   {
-    PhaseTimer pt(ctx, PH_MSM_ACCUMULATE);
+    PhaseTimer pt(ctx, PH_MSM_ACCUMULATE, st);
     unsigned blocks = (nbuckets + 127) / 128;
-    msm_accumulate_kernel<<<blocks, 128, 0, st>>>(base_ptr, starts, sorted, order, sh, nbuckets, ctx->msm_buckets.p);
+    msm_accumulate_kernel<<<blocks, 128, 0, st>>>(base_ptr, starts, sorted, order, sh, nbuckets, ws.msm_buckets.p);
     B200ZK_LAUNCH_CHECK(ctx, "msm_accumulate_kernel");
   }
   {
-    PhaseTimer pt(ctx, PH_MSM_BIG);
+    PhaseTimer pt(ctx, PH_MSM_BIG, st);
     unsigned blocks = (nbuckets + 255) / 256;
     msm_big_list_kernel<<<blocks, 256, 0, st>>>(starts, nbuckets, sh, plan, big_bucket, big_first, big_cap, chunk_bucket,
                                                 chunk_idx);
     B200ZK_LAUNCH_CHECK(ctx, "msm_big_list_kernel");
     const size_t shm = BIG_THREADS * sizeof(G1XYZZ);
     msm_big_accumulate_kernel<<<ctx->sm_count * 4, BIG_THREADS, 0, st>>>(base_ptr, starts, sorted, plan, chunk_bucket,
-                                                                       chunk_idx, ctx->msm_big.p);
+                                                                       chunk_idx, ws.msm_big.p);
     B200ZK_LAUNCH_CHECK(ctx, "msm_big_accumulate_kernel");
     msm_big_reduce_kernel<<<ctx->sm_count, BIG_THREADS, shm, st>>>(starts, plan, big_bucket, big_first, big_cap,
-                                                                   ctx->msm_big.p, ctx->msm_buckets.p);
+                                                                   ws.msm_big.p, ws.msm_buckets.p);
     B200ZK_LAUNCH_CHECK(ctx, "msm_big_reduce_kernel");
   }
   {
-    PhaseTimer pt(ctx, PH_MSM_REDUCE);
+    PhaseTimer pt(ctx, PH_MSM_REDUCE, st);
     const unsigned tot1 = sh.nsets * chunks_per_set;
     if (chunk_log == CHUNK_LOG_SMALL)
-      msm_reduce_r1_kernel<CHUNK_LOG_SMALL><<<(tot1 + 127) / 128, 128, 0, st>>>(ctx->msm_buckets.p, tot1, run, acc);
+      msm_reduce_r1_kernel<CHUNK_LOG_SMALL><<<(tot1 + 127) / 128, 128, 0, st>>>(ws.msm_buckets.p, tot1, run, acc);
     else
-      msm_reduce_r1_kernel<CHUNK_LOG><<<(tot1 + 127) / 128, 128, 0, st>>>(ctx->msm_buckets.p, tot1, run, acc);
+      msm_reduce_r1_kernel<CHUNK_LOG><<<(tot1 + 127) / 128, 128, 0, st>>>(ws.msm_buckets.p, tot1, run, acc);
     B200ZK_LAUNCH_CHECK(ctx, "msm_reduce_r1_kernel");
     const size_t shm = BIG_THREADS * sizeof(G1XYZZ);
     dim3 grid2(nslices, nplanes, sh.nsets);
@@ -911,7 +912,7 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
     B200ZK_LAUNCH_CHECK(ctx, "msm_reduce_r3_kernel");
   }
   {
-    PhaseTimer pt(ctx, PH_MSM_FINAL);
+    PhaseTimer pt(ctx, PH_MSM_FINAL, st);
     msm_final_kernel<<<1, 32, 0, st>>>(set_sums, sh, out_dev, out_kind);
     B200ZK_LAUNCH_CHECK(ctx, "msm_final_kernel");
   }

@@ -607,6 +607,25 @@ int commit(b200zk_ctx* ctx, const b200zk_plonk_pk* pk, const uint4* poly, size_t
   return msm_run(ctx, pk->bases, 0, poly, len, out, 0);
 }
 
+// several independent commitments (one prover round): each on its own MSM lane of the context, so the latency-bound
+// phases of one MSM run under the bucket accumulation of another; everything is joined back into the context stream
+int commit_many(b200zk_ctx* ctx, const b200zk_plonk_pk* pk, const uint4* const* polys, const size_t* lens, const int* slots,
+                int count) {
+  if (pk->commit_hook || count == 1 || ctx->msm_single_lane) {
+    for (int k = 0; k < count; k++) B200ZK_TRY(commit(ctx, pk, polys[k], lens[k], slots[k]));
+    return B200ZK_OK;
+  }
+  B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+  for (int l = 1; l < MSM_LANES && l < count; l++) B200ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->ws[l].stream, ctx->ev_fork, 0));
+  for (int k = 0; k < count; k++)
+    B200ZK_TRY(msm_run(ctx, pk->bases, 0, polys[k], lens[k], (char*)pk->points + 64 * slots[k], 0, k % MSM_LANES));
+  for (int l = 1; l < MSM_LANES && l < count; l++) {
+    B200ZK_CUDA(ctx, cudaEventRecord(ctx->ws[l].done, ctx->ws[l].stream));
+    B200ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ws[l].done, 0));
+  }
+  return B200ZK_OK;
+}
+
 int fetch_points(b200zk_ctx* ctx, const b200zk_plonk_pk* pk, int first, int count, uint8_t* out) {
   B200ZK_CUDA(ctx, cudaMemcpyAsync(out, (char*)pk->points + 64 * first, 64 * (size_t)count, cudaMemcpyDeviceToHost,
                                    ctx->stream));
@@ -747,7 +766,11 @@ int b200zk_plonk_setup(b200zk_ctx* ctx, const b200zk_bases* bases, unsigned log2
   PK_TRY(to_canonical(ctx, pk->s3, log2n));
   // verifying-key commitments: S1,S2,S3,Ql,Qr,Qm,Qo,Qk
   const uint4* cpoly[8] = {pk->s1, pk->s2, pk->s3, pk->ql, pk->qr, pk->qm, pk->qo, pk->cqk};
-  for (int i = 0; i < 8; i++) PK_TRY(commit(ctx, pk, cpoly[i], n, i));
+  {
+    const size_t clen[8] = {n, n, n, n, n, n, n, n};
+    const int cslot[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+    PK_TRY(commit_many(ctx, pk, cpoly, clen, cslot, 8));
+  }
   PK_TRY(fetch_points(ctx, pk, 0, 8, pk->vk_points));
   PK_CUDA(cudaMemcpyAsync((char*)pk->points + 64 * 16, pk->points, 8 * 64, cudaMemcpyDeviceToDevice, st));
   // Lagrange-coset forms on the big domain (gnark: computeLagrangeCosetPolys at key load)
@@ -894,7 +917,11 @@ static int prove_impl(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solution
     k_blind<<<1, 32, 0, st>>>(can[k], n, pk->blinding + 2 * (2 * k), 2);
     B200ZK_LAUNCH_CHECK(ctx, "k_blind");
   }
-  for (int k = 0; k < 3; k++) B200ZK_TRY(commit(ctx, pk, can[k], n + 2, 8 + k));
+  {
+    const size_t clen[3] = {n + 2, n + 2, n + 2};
+    const int cslot[3] = {8, 9, 10};
+    B200ZK_TRY(commit_many(ctx, pk, can, clen, cslot, 3));
+  }
   B200ZK_TRY(fetch_points(ctx, pk, 8, 3, pts));  // pts[0..2] = LRO (the sync also lands bad_row)
   pk->last_bad_row = bad_row == 0xffffffffu ? -1 : (long long)bad_row;
   if (pk->last_bad_row >= 0) return B200ZK_ERR_UNSATISFIED;
@@ -994,7 +1021,12 @@ static int prove_impl(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solution
 
   // P12: commit h1, h2, h3
   const size_t m = n + 2;
-  for (int k = 0; k < 3; k++) B200ZK_TRY(commit(ctx, pk, pk->t + 2 * (k * m), m, 12 + k));
+  {
+    const uint4* hp[3] = {pk->t, pk->t + 2 * m, pk->t + 4 * m};
+    const size_t clen[3] = {m, m, m};
+    const int cslot[3] = {12, 13, 14};
+    B200ZK_TRY(commit_many(ctx, pk, hp, clen, cslot, 3));
+  }
   B200ZK_TRY(fetch_points(ctx, pk, 12, 3, pts + 64 * 4));  // pts[4..6] = H
   fs.begin("zeta");
   for (int i = 0; i < 3; i++) fs.bind_point(pts + 64 * (4 + i));

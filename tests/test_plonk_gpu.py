@@ -223,3 +223,24 @@ def test_2_20_rows_byte_identical_to_the_c_port(ctx):
     assert pl.verify(pl.Proof.from_bytes(proof.to_gnark_bytes()), vk, [c["x0"]], (pl.G2_GEN, pl.g2_mul(pl.G2_GEN, ALPHA)))
     pk_d.close()
     srs_d.close()
+
+
+def test_commit_lanes_do_not_change_the_proof(ctx):
+    """the three commitments of a round on three MSM lanes vs one after the other: same key, same proof bytes"""
+    lib = zk.load()
+    cs_o, x = pl.synthetic_chain_circuit(3000, 0xB2000004, 1)
+    blind = blinding_bytes(11)
+    blobs, vks = [], []
+    try:
+        for lanes in (1, 3):
+            lib.b200zk_plonk_set_commit_lanes(ctx.handle, lanes)
+            srs_d = zk.SRS.NewSRS(5000, o.fr_to_mont_bytes([ALPHA]), ctx).precompute()
+            pk_d = zkp.ProvingKey.Setup(to_product_cs(cs_o), srs_d, ctx)
+            vks.append(pk_d.vk_points)
+            blobs.append([pk_d.Prove(o.fr_to_mont_bytes(x), blind).blob for _ in range(3)])
+            pk_d.close()
+            srs_d.close()
+    finally:
+        lib.b200zk_plonk_set_commit_lanes(ctx.handle, 3)
+    assert vks[0] == vks[1]
+    assert len({b for bs in blobs for b in bs}) == 1
