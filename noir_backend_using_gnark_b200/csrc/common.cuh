@@ -72,6 +72,7 @@ struct b200zk_ctx {
   cudaEvent_t ev_chunk[8] = {};  // host-scalar MSM: chunk i of the scalars has landed (copy stream -> compute stream)
   int msm_host_chunks = 0;       // 0 = choose from n; 1 = never split (tests / tuning)
   int msm_chunk_log = 0;         // tests / tuning: force the running-sum chunk size of the bucket reduction (3 or 5)
+  bool lane_pending = false;     // a forked commitment is in flight on MSM lane 1
   int msm_single_lane = 0;       // tests / tuning: the prover's commitment rounds run one MSM after the other
   int msm_no_tiny = 0;           // tests: force the bucket pipeline also for small table-mode MSMs
   uint64_t launches = 0;

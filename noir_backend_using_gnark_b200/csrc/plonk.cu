@@ -626,6 +626,24 @@ int commit_many(b200zk_ctx* ctx, const b200zk_plonk_pk* pk, const uint4* const* 
   return B200ZK_OK;
 }
 
+// one commitment on MSM lane 1 while the context stream continues with work that neither needs its result nor
+// rewrites its input; commit_join() orders the context stream after it
+int commit_fork(b200zk_ctx* ctx, const b200zk_plonk_pk* pk, const uint4* poly, size_t len, int slot) {
+  if (pk->commit_hook || ctx->msm_single_lane) return commit(ctx, pk, poly, len, slot);
+  B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+  B200ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->ws[1].stream, ctx->ev_fork, 0));
+  B200ZK_TRY(msm_run(ctx, pk->bases, 0, poly, len, (char*)pk->points + 64 * slot, 0, 1));
+  B200ZK_CUDA(ctx, cudaEventRecord(ctx->ws[1].done, ctx->ws[1].stream));
+  ctx->lane_pending = true;
+  return B200ZK_OK;
+}
+int commit_join(b200zk_ctx* ctx) {
+  if (!ctx->lane_pending) return B200ZK_OK;
+  ctx->lane_pending = false;
+  B200ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ws[1].done, 0));
+  return B200ZK_OK;
+}
+
 int fetch_points(b200zk_ctx* ctx, const b200zk_plonk_pk* pk, int first, int count, uint8_t* out) {
   B200ZK_CUDA(ctx, cudaMemcpyAsync(out, (char*)pk->points + 64 * first, 64 * (size_t)count, cudaMemcpyDeviceToHost,
                                    ctx->stream));
@@ -957,11 +975,9 @@ static int prove_impl(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solution
   B200ZK_TRY(to_canonical(ctx, pk->bz, log2n));
   k_blind<<<1, 32, 0, st>>>(pk->bz, n, pk->blinding + 2 * 6, 3);
   B200ZK_LAUNCH_CHECK(ctx, "k_blind");
-  B200ZK_TRY(commit(ctx, pk, pk->bz, n + 3, 11));
-  B200ZK_TRY(fetch_points(ctx, pk, 11, 1, pts + 64 * 3));  // pts[3] = Z
-  fs.begin("alpha");
-  fs.bind_point(pts + 64 * 3);
-  const Fe4 alpha = fs.finish();
+  // the commitment to Z runs on an MSM lane of its own while the context stream prepares what the quotient needs and
+  // that does not depend on alpha (P8, P9)
+  B200ZK_TRY(commit_fork(ctx, pk, pk->bz, n + 3, 11));
 
   // P8: qk completed with the public inputs, canonical
   B200ZK_CUDA(ctx, cudaMemcpyAsync(pk->qk, pk->lqk, n * 32, cudaMemcpyDeviceToDevice, st));
@@ -977,6 +993,12 @@ static int prove_impl(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solution
   B200ZK_TRY(to_coset(ctx, pk->bo, n + 2, pk->eo, logb));
   B200ZK_TRY(to_coset(ctx, pk->bz, n + 3, pk->ez, logb));
   B200ZK_TRY(to_coset(ctx, pk->qk, n, pk->eqk, logb));
+
+  B200ZK_TRY(commit_join(ctx));
+  B200ZK_TRY(fetch_points(ctx, pk, 11, 1, pts + 64 * 3));  // pts[3] = Z
+  fs.begin("alpha");
+  fs.bind_point(pts + 64 * 3);
+  const Fe4 alpha = fs.finish();
 
   // P10-P11: quotient numerator / (X^n - 1), then back to canonical
   {
@@ -1103,7 +1125,7 @@ static int prove_impl(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solution
 
   // P14: opening of Z at w*zeta
   B200ZK_TRY(divide_x_minus_a(ctx, pk, pk->bz, n + 3, zeta_shift, pk->quot));
-  B200ZK_TRY(commit(ctx, pk, pk->quot, n + 2, 15));  // ZShiftedOpening.H
+  B200ZK_TRY(commit_fork(ctx, pk, pk->quot, n + 2, 15));  // ZShiftedOpening.H, on its own lane until the fetch below
 
   // P15: linearised polynomial
   {
@@ -1126,6 +1148,7 @@ static int prove_impl(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solution
   B200ZK_TRY(eval_poly(ctx, pk, pk->folded_h, m, zeta, 6));
   B200ZK_TRY(eval_poly(ctx, pk, pk->lin, n + 3, zeta, 7));
   B200ZK_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));  // join the side stream (digests)
+  B200ZK_TRY(commit_join(ctx));  // ... and the lane of ZShiftedOpening.H (pk->quot is rewritten below)
   B200ZK_TRY(fetch_scalars(ctx, pk, 6, 2, sc + 6));
   B200ZK_TRY(fetch_points(ctx, pk, 0, 2, pts + 64 * 9));  // pts[9] = lin digest, pts[10] = folded H digest
   B200ZK_TRY(fetch_points(ctx, pk, 15, 1, pts + 64 * 8));  // pts[8] = ZShiftedOpening.H
