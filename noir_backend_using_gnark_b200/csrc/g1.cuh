@@ -172,4 +172,18 @@ static __device__ __noinline__ G1Affine g1_to_affine(G1XYZZ p) {
   return r;
 }
 
+// the same for code in which a single thread normalises one point (see fe_inv_single)
+static __device__ __noinline__ G1Affine g1_to_affine_single(G1XYZZ p) {
+  G1Affine r;
+  if (g1_is_inf(p)) {
+    r.x = fe_zero<FpParams>();
+    r.y = fe_zero<FpParams>();
+    return r;
+  }
+  Fp inv = fe_inv_single(fe_mul(p.zz, p.zzz));
+  r.x = fe_mul(fe_mul(p.x, p.zzz), inv);
+  r.y = fe_mul(fe_mul(p.y, p.zz), inv);
+  return r;
+}
+
 }  // namespace b200zk

@@ -520,7 +520,7 @@ __global__ void __launch_bounds__(BIG_THREADS) msm_tiny_final_kernel(const void*
   }
   block_reduce_xyzz(acc, sh_pts);
   if (threadIdx.x == 0) {
-    if (out_kind == 0) g1_store_affine(out, 0, g1_to_affine(acc));
+    if (out_kind == 0) g1_store_affine(out, 0, g1_to_affine_single(acc));
     else g1_store_xyzz(out, 0, acc);
   }
 }
@@ -537,7 +537,7 @@ __global__ void msm_final_kernel(const void* __restrict__ set_sums, MsmShape sh,
     g1_add(total, q);
   }
   if (out_kind == 0) {
-    G1Affine r = g1_to_affine(total);
+    G1Affine r = g1_to_affine_single(total);
     g1_store_affine(out, 0, r);
   } else {
     g1_store_xyzz(out, 0, total);
@@ -551,7 +551,7 @@ __global__ void g1_sum_kernel(const void* __restrict__ partials, unsigned count,
     G1XYZZ q = g1_load_xyzz(partials, i);
     g1_add(total, q);
   }
-  G1Affine r = g1_to_affine(total);
+  G1Affine r = g1_to_affine_single(total);
   g1_store_affine(out, 0, r);
 }
 

@@ -511,7 +511,7 @@ __global__ void k_small_msm(SmallMsmArgs a0, void* out0, SmallMsmArgs a1, void* 
     }
     g1_add(acc, o);
   }
-  if (lane == 0) g1_store_affine(out, 0, g1_to_affine(acc));
+  if (lane == 0) g1_store_affine(out, 0, g1_to_affine_single(acc));
 }
 
 }  // namespace b200zk
