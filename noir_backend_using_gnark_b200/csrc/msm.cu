@@ -649,7 +649,9 @@ int msm_precompute_run(b200zk_ctx* ctx, b200zk_bases* bases, int c_req) {
   else if (lg >= 15) W = 15;   // widths 17 x15           -> 2^16 buckets
   else if (lg >= 14) W = 16;   // widths 16 x15, 15       -> 2^15 buckets
   else if (lg >= 13) W = 17;   // widths 15 x17           -> 2^14 buckets
-  else W = 20;                 // widths 13 x15, 12 x5    -> 2^12 buckets (mostly served by the small path)
+  else if (lg >= 11) W = 20;   // widths 13 x15, 12 x5    -> 2^12 buckets (mostly served by the small path)
+  else W = 43;                 // widths 6               -> the small path multiplies by 6-bit digits: its latency is
+                               //                           the double-and-add chain, the table is tiny anyway
   // (measured per size with scripts/table_window_sweep.py: below 2^19 points the bucket count decides the latency —
   //  too few buckets leave the accumulation with a handful of long serial runs, too many make the reduction dominate)
   if (W > MAX_WINDOWS) W = MAX_WINDOWS;
