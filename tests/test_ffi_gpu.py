@@ -171,3 +171,24 @@ def test_value_payload_edge_cases_on_the_device_decoder(home):
     assert rc == 1 and "hex" in err, (rc, err)
     rc, res, err = run_child(steps[:1] + [{"op": "raw_prove", "acir": js, "values": plain[:-64], "pk": "@0.pk"}], home, env)
     assert rc == 1, (rc, err)      # no values: different key size / unsatisfied system, fatal either way
+
+
+def test_key_cache_eviction_and_alternating_circuits(home):
+    """two circuits through one process with room for a single cached key (B200ZK_FFI_CACHE=1): every switch evicts the
+    other circuit's parsed ACIR and device-resident key and rebuilds them; proofs stay byte-identical to the oracle's."""
+    env = {"B200ZK_BLINDING_SEED": str(SEED), "B200ZK_FFI_CACHE": "1"}
+    srs = pl.SRS(128, 0xB2000005)
+    want, steps = {}, []
+    for idx in (0, 2):
+        js, vals = FIXTURES[idx]
+        vals = [v % o.R_MOD for v in vals]
+        cs, pub, sec = pl.build_sparse_r1cs(pl.decode_acir(js), vals)
+        pk = pl.setup(cs, srs)
+        want[idx] = (pl.prove(cs, pk, srs, pub + sec, pl.BlindingStream(SEED)).to_bytes().hex(), ff.pk_bytes(pk).hex())
+    order = [0, 2, 0, 2, 2, 0]
+    for idx in order:
+        js, vals = FIXTURES[idx]
+        steps.append({"op": "prove", "acir": js, "values": [str(v % o.R_MOD) for v in vals], "pk": want[idx][1]})
+    rc, res, err = run_child(steps, home, env)
+    assert rc == 0, err
+    assert res == [want[idx][0] for idx in order]
