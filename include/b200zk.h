@@ -142,7 +142,8 @@ int b200zk_msm_set_flat_scatter(b200zk_ctx* ctx, int on);
  * under the MSM of the previous one; 0 = choose from n (2 chunks from 2^23 points: measured best, scripts/e2e_chunks.py), 1 = never split, up to 8 */
 int b200zk_msm_set_host_chunks(b200zk_ctx* ctx, int chunks);
 /* tests / tuning: buckets per running-sum chunk of the bucket reduction, as a power of two: 3 (short dependent chains,
- * chosen up to 2^17 buckets where the reduction is latency-bound), 5 (fewer chunk results, chosen above), 0 = automatic */
+ * chosen up to 2^17 buckets where the reduction is latency-bound), 4 (up to 2^19 buckets), 5 (fewer chunk results, chosen
+ * above), 0 = automatic (measured: scripts/reduce_chunk_sweep.py) */
 int b200zk_msm_set_reduce_chunk(b200zk_ctx* ctx, int chunk_log);
 /* tests: with a window table, MSMs of up to 2^17 (point, window) terms skip the bucket pipeline (one thread per term,
  * two launches: the sizes of the reference's own test circuits); 0 forces the bucket pipeline there too, 1 = default */

@@ -356,7 +356,7 @@ int b200zk_plonk_set_commit_lanes(b200zk_ctx* ctx, int lanes) {
 }
 
 int b200zk_msm_set_reduce_chunk(b200zk_ctx* ctx, int chunk_log) {
-  if (!ctx || (chunk_log != 0 && chunk_log != 3 && chunk_log != 5)) return B200ZK_ERR_BAD_ARG;
+  if (!ctx || (chunk_log != 0 && chunk_log != 3 && chunk_log != 4 && chunk_log != 5)) return B200ZK_ERR_BAD_ARG;
   ctx->msm_chunk_log = chunk_log;
   return B200ZK_OK;
 }

@@ -775,7 +775,8 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
   }
   // short chunks while the bucket count is small enough for the bit-plane sums to stay cheap
   const unsigned chunk_log = (ctx->msm_chunk_log ? (unsigned)ctx->msm_chunk_log
-                                                 : ((size_t)nbuckets <= ((size_t)1 << 17) ? CHUNK_LOG_SMALL : CHUNK_LOG));
+                                                 : ((size_t)nbuckets <= ((size_t)1 << 17) ? CHUNK_LOG_SMALL
+                                                    : (size_t)nbuckets <= ((size_t)1 << 19) ? 4 : CHUNK_LOG));
   const unsigned chunks_per_set = sh.B >> chunk_log;
   unsigned chunk_bits = 0;
   while ((1u << chunk_bits) < chunks_per_set) chunk_bits++;
@@ -903,6 +904,8 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
     const unsigned tot1 = sh.nsets * chunks_per_set;
     if (chunk_log == CHUNK_LOG_SMALL)
       msm_reduce_r1_kernel<CHUNK_LOG_SMALL><<<(tot1 + 127) / 128, 128, 0, st>>>(ws.msm_buckets.p, tot1, run, acc);
+    else if (chunk_log == 4)
+      msm_reduce_r1_kernel<4><<<(tot1 + 127) / 128, 128, 0, st>>>(ws.msm_buckets.p, tot1, run, acc);
     else
       msm_reduce_r1_kernel<CHUNK_LOG><<<(tot1 + 127) / 128, 128, 0, st>>>(ws.msm_buckets.p, tot1, run, acc);
     B200ZK_LAUNCH_CHECK(ctx, "msm_reduce_r1_kernel");

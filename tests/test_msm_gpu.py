@@ -404,7 +404,7 @@ def test_bucket_reduction_chunk_sizes_agree(ctx, log2n):
         for table in (False, True):
             if table:
                 srs.precompute()
-            for cl in (3, 5, 0):
+            for cl in (3, 4, 5, 0):
                 lib.b200zk_msm_set_reduce_chunk(ctx.handle, cl)
                 assert zk.MultiExp(srs, sc) == want, (table, cl)
     finally:
