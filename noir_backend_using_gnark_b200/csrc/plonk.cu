@@ -11,6 +11,7 @@
 #include "consts.cuh"
 #include "g1.cuh"
 #include "host_field.h"
+#include "ffi/bn254_host.h"  // host G1 arithmetic (Straus) for the two homomorphic digests
 
 namespace b200zk {
 
@@ -464,54 +465,6 @@ __global__ void __launch_bounds__(256) k_fold7(FoldArgs a) {
   for (int i = 1; i < 7; i++)
     if (j < a.len[i]) v = fe_add(v, fe_mul(fe_load_ro<FrParams>(a.p[i] + 2 * j), arg(a.gpow[i])));
   fe_store(a.out + 2 * j, v);
-}
-
-// out = sum_k scalars[k] * points[k] for a handful of points (k < 32): lane k does double-and-add over its
-// regular-form scalar, the lanes are summed with a warp-shuffle tree.  Used for the homomorphic digests
-// (folded H, linearised polynomial) that gnark obtains from existing commitments or a full MSM.
-struct SmallMsmArgs {
-  const void* points[8];   // each a G1Affine (64 B) in device memory
-  FrArg scalars[8];        // regular form
-  unsigned count;
-};
-// two independent digests in one launch (one warp-sized CTA each): they are latency-bound, so running them side by
-// side halves their contribution to the critical path of small circuits
-__global__ void k_small_msm(SmallMsmArgs a0, void* out0, SmallMsmArgs a1, void* out1) {
-  const SmallMsmArgs& a = blockIdx.x == 0 ? a0 : a1;
-  void* out = blockIdx.x == 0 ? out0 : out1;
-  const unsigned lane = threadIdx.x & 31;
-  // 4-bit fixed windows: the lane's multiples 1P..15P live in shared memory, so the 256 doublings are followed by 64
-  // additions instead of one (divergent) addition per bit
-  __shared__ G1XYZZ multiples[8][15];
-  G1XYZZ acc = g1_xyzz_inf();
-  if (lane < a.count) {
-    const G1Affine p = g1_load_affine(a.points[lane], 0);
-    G1XYZZ m = g1_xyzz_inf();
-    for (int k = 0; k < 15; k++) {
-      g1_add_mixed(m, p);
-      multiples[lane][k] = m;
-    }
-    for (int w = 63; w >= 0; w--) {
-      g1_double(acc);
-      g1_double(acc);
-      g1_double(acc);
-      g1_double(acc);
-      const unsigned d = (a.scalars[lane].l[w >> 3] >> (4 * (w & 7))) & 15u;
-      if (d) g1_add(acc, multiples[lane][d - 1]);
-    }
-  }
-  for (int d = 16; d > 0; d >>= 1) {
-    G1XYZZ o;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-      o.x.l[i] = __shfl_xor_sync(0xffffffffu, acc.x.l[i], d);
-      o.y.l[i] = __shfl_xor_sync(0xffffffffu, acc.y.l[i], d);
-      o.zz.l[i] = __shfl_xor_sync(0xffffffffu, acc.zz.l[i], d);
-      o.zzz.l[i] = __shfl_xor_sync(0xffffffffu, acc.zzz.l[i], d);
-    }
-    g1_add(acc, o);
-  }
-  if (lane == 0) g1_store_affine(out, 0, g1_to_affine_single(acc));
 }
 
 }  // namespace b200zk
@@ -1086,43 +1039,6 @@ static int prove_impl(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solution
   lagv = M(M(M(lagv, alpha), alpha), host::inv(HFR, host::from_u64(HFR, (uint64_t)n)));
   const Fe4 zpm = host::pow_u64(HFR, zeta, (uint64_t)m);
 
-  // The two homomorphic digests are single-warp, latency-bound kernels: run them on the side stream so they overlap
-  // the opening MSM below instead of sitting on the critical path.
-  B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
-  B200ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
-  SmallMsmArgs sm_lin, sm_fold;
-  {
-    // digest of the linearised polynomial from the commitments it is a linear combination of (what the verifier
-    // does; equal to kzg.Commit(lin) because the commitment is linear) instead of a full (n+3)-point MSM:
-    //   l*[Ql] + r*[Qr] + l*r*[Qm] + o*[Qo] + [Qk] + alpha*c1*[S3] + (alpha*c2 + lag)*[Z]
-    SmallMsmArgs& sm = sm_lin;
-    char* vkd = (char*)pk->points + 64 * 16;  // device copy of the vk points (uploaded at setup)
-    const void* pp[7] = {vkd + 64 * 3, vkd + 64 * 4, vkd + 64 * 5, vkd + 64 * 6, vkd + 64 * 7, vkd + 64 * 2,
-                         (char*)pk->points + 64 * 11};
-    const Fe4 ss[7] = {lz, rz, M(lz, rz), oz, HFR.one, M(alpha, c1), A(M(alpha, c2), lagv)};
-    for (int i = 0; i < 7; i++) {
-      sm.points[i] = pp[i];
-      sm.scalars[i] = to_arg(host::from_mont(HFR, ss[i]));
-    }
-    sm.points[7] = pp[0];
-    sm.scalars[7] = to_arg(Fe4{{0, 0, 0, 0}});
-    sm.count = 7;
-  }
-  {
-    // foldedHDigest = H0 + zpm*H1 + zpm^2*H2
-    SmallMsmArgs& sm = sm_fold;
-    const Fe4 ss[3] = {HFR.one, zpm, M(zpm, zpm)};
-    for (int i = 0; i < 8; i++) {
-      sm.points[i] = (char*)pk->points + 64 * (12 + (i < 3 ? i : 0));
-      sm.scalars[i] = to_arg(i < 3 ? host::from_mont(HFR, ss[i]) : Fe4{{0, 0, 0, 0}});
-    }
-    sm.count = 3;
-  }
-  // slot 0: linearised polynomial digest, slot 1: folded H digest
-  k_small_msm<<<2, 32, 0, ctx->side>>>(sm_lin, (char*)pk->points + 64 * 0, sm_fold, (char*)pk->points + 64 * 1);
-  B200ZK_LAUNCH_CHECK(ctx, "k_small_msm");
-  B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side));
-
   // P14: opening of Z at w*zeta
   B200ZK_TRY(divide_x_minus_a(ctx, pk, pk->bz, n + 3, zeta_shift, pk->quot));
   B200ZK_TRY(commit_fork(ctx, pk, pk->quot, n + 2, 15));  // ZShiftedOpening.H, on its own lane until the fetch below
@@ -1147,10 +1063,27 @@ static int prove_impl(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solution
   // P17: batch opening at zeta of [foldedH, lin, L, R, O, S1, S2]
   B200ZK_TRY(eval_poly(ctx, pk, pk->folded_h, m, zeta, 6));
   B200ZK_TRY(eval_poly(ctx, pk, pk->lin, n + 3, zeta, 7));
-  B200ZK_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));  // join the side stream (digests)
-  B200ZK_TRY(commit_join(ctx));  // ... and the lane of ZShiftedOpening.H (pk->quot is rewritten below)
+  // While the device works through the queue above, the host forms the two homomorphic digests from commitments it
+  // already holds (what the verifier does; equal to kzg.Commit of the polynomials because the commitment is linear,
+  // so no (n+3)-point MSM and no kernel at all):
+  //   lin     = l*[Ql] + r*[Qr] + l*r*[Qm] + o*[Qo] + [Qk] + alpha*c1*[S3] + (alpha*c2 + lag)*[Z]      -> pts[9]
+  //   foldedH = [H0] + zeta^(n+2)*[H1] + zeta^(2(n+2))*[H2]                                            -> pts[10]
+  {
+    namespace hf = b200zk::ffi;
+    const uint8_t* vkp = pk->vk_points;  // S0,S1,S2,Ql,Qr,Qm,Qo,Qk
+    const std::vector<hf::G1> lp = {hf::g1_from_image(vkp + 64 * 3), hf::g1_from_image(vkp + 64 * 4),
+                                    hf::g1_from_image(vkp + 64 * 5), hf::g1_from_image(vkp + 64 * 6),
+                                    hf::g1_from_image(vkp + 64 * 2), hf::g1_from_image(pts + 64 * 3)};
+    const std::vector<Fe4> ls = {lz, rz, M(lz, rz), oz, M(alpha, c1), A(M(alpha, c2), lagv)};
+    hf::g1_to_image(hf::g1j_to_affine(hf::g1j_add_affine(hf::g1_msm_small(lp, ls), hf::g1_from_image(vkp + 64 * 7))),
+                    pts + 64 * 9);
+    const std::vector<hf::G1> hp = {hf::g1_from_image(pts + 64 * 5), hf::g1_from_image(pts + 64 * 6)};
+    const std::vector<Fe4> hs = {zpm, M(zpm, zpm)};
+    hf::g1_to_image(hf::g1j_to_affine(hf::g1j_add_affine(hf::g1_msm_small(hp, hs), hf::g1_from_image(pts + 64 * 4))),
+                    pts + 64 * 10);
+  }
+  B200ZK_TRY(commit_join(ctx));  // the lane of ZShiftedOpening.H (pk->quot is rewritten below)
   B200ZK_TRY(fetch_scalars(ctx, pk, 6, 2, sc + 6));
-  B200ZK_TRY(fetch_points(ctx, pk, 0, 2, pts + 64 * 9));  // pts[9] = lin digest, pts[10] = folded H digest
   B200ZK_TRY(fetch_points(ctx, pk, 15, 1, pts + 64 * 8));  // pts[8] = ZShiftedOpening.H
   const Fe4 claimed[7] = {sc[6], sc[7], lz, rz, oz, s1z, s2z};
   Transcript kz;
