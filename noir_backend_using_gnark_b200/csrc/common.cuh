@@ -67,7 +67,7 @@ struct b200zk_ctx {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
-  cudaStream_t side = nullptr;  // latency-bound single-warp work that overlaps the big kernels (prover digests)
+  cudaStream_t side = nullptr;  // copy stream of the host-scalar MSM (chunk i+1 lands while chunk i is processed)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev_chunk[8] = {};  // host-scalar MSM: chunk i of the scalars has landed (copy stream -> compute stream)
   int msm_host_chunks = 0;       // 0 = choose from n; 1 = never split (tests / tuning)
