@@ -287,6 +287,7 @@ void b200zk_bases_free(b200zk_ctx* ctx, b200zk_bases* bases) {
       cudaStreamSynchronize(ctx->stream);
     }
     cudaFree(bases->table);
+    if (bases->small_table) cudaFree(bases->small_table);
   }
   delete bases;
 }

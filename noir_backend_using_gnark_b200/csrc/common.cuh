@@ -61,6 +61,11 @@ struct b200zk_bases {
   void* table = nullptr;
   unsigned tab_c = 0, tab_W = 0;
   uint8_t tab_wstart[65] = {0};  // window j covers scalar bits [tab_wstart[j], tab_wstart[j+1])
+  // narrow-window table of the first small_n bases (large base sets only): what small MSMs use
+  void* small_table = nullptr;
+  size_t small_n = 0;
+  unsigned small_c = 0;
+  uint8_t small_wstart[65] = {0};
 };
 
 struct b200zk_ctx {

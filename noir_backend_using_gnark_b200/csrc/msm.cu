@@ -30,7 +30,9 @@ static constexpr int CHUNK = 1 << CHUNK_LOG;   // 2^3 for small bucket counts, w
 static constexpr int CHUNK_LOG_SMALL = 3;
 static constexpr int BIG_CHUNK = 8192;         // sorted entries per CTA in the long-run path
 static constexpr int BIG_THREADS = 256;
-static constexpr size_t TINY_MAX_TERMS = (size_t)1 << 17;  // (points x windows) up to which the bucket pipeline is skipped
+static constexpr size_t TINY_MAX_TERMS = (size_t)1 << 17;
+static constexpr unsigned SMALL_TABLE_W = 43;     // 6-bit windows
+static constexpr size_t SMALL_TABLE_N = 2048;     // head of a large base set that also gets the narrow-window table  // (points x windows) up to which the bucket pipeline is skipped
 static constexpr int MAX_WINDOWS = 64;
 static constexpr int SLICE = 1024;             // chunk results per CTA in the bit-plane sums
 static constexpr int MAX_PLANES = 24;
@@ -633,28 +635,9 @@ static unsigned choose_window(size_t n) {
   return 8;
 }
 
-int msm_precompute_run(b200zk_ctx* ctx, b200zk_bases* bases, int c_req) {
-  if (!bases || !bases->dev) return B200ZK_ERR_BAD_ARG;
-  if (bases->table) return B200ZK_OK;
-  const size_t n = bases->n;
-  if (n == 0) return B200ZK_OK;
-  unsigned lg = 0;
-  while (((size_t)1 << (lg + 1)) <= n) lg++;
-  // number of windows from the size (or from a requested maximum width c_req): W windows of 255/W bits (+1 for the
-  // first 255 % W of them)
-  unsigned W;
-  if (c_req) W = (255 + (unsigned)c_req - 1) / (unsigned)c_req;
-  else if (lg >= 23) W = 12;   // widths 22,22,22,21 x9  -> 2^21 buckets
-  else if (lg >= 19) W = 13;   // widths 20 x8, 19 x5     -> 2^19 buckets
-  else if (lg >= 15) W = 15;   // widths 17 x15           -> 2^16 buckets
-  else if (lg >= 14) W = 16;   // widths 16 x15, 15       -> 2^15 buckets
-  else if (lg >= 13) W = 17;   // widths 15 x17           -> 2^14 buckets
-  else if (lg >= 11) W = 20;   // widths 13 x15, 12 x5    -> 2^12 buckets (mostly served by the small path)
-  else W = 43;                 // widths 6               -> the small path multiplies by 6-bit digits: its latency is
-                               //                           the double-and-add chain, the table is tiny anyway
-  // (measured per size with scripts/table_window_sweep.py: below 2^19 points the bucket count decides the latency —
-  //  too few buckets leave the accumulation with a handful of long serial runs, too many make the reduction dominate)
-  if (W > MAX_WINDOWS) W = MAX_WINDOWS;
+// table[j*n + i] = 2^wstart[j] * P_i for W windows splitting the 255 scalar bits evenly (+1 bit for the first 255 % W)
+static int build_window_table(b200zk_ctx* ctx, const void* points, size_t n, unsigned W, void** table_out, uint8_t* wstart_out,
+                              unsigned* c_out) {
   MsmShape tsh;
   memset(&tsh, 0, sizeof(tsh));
   tsh.W = W;
@@ -668,7 +651,6 @@ int msm_precompute_run(b200zk_ctx* ctx, b200zk_bases* bases, int c_req) {
     tsh.wstart[W] = 255;
     tsh.c = base + (rem ? 1 : 0);
   }
-  const unsigned c = tsh.c;
   if ((size_t)W * n >= ((size_t)1 << 31)) return B200ZK_ERR_UNSUPPORTED;
   void* table = nullptr;
   cudaError_t e = cudaMalloc(&table, (size_t)W * n * 64);
@@ -680,7 +662,7 @@ int msm_precompute_run(b200zk_ctx* ctx, b200zk_bases* bases, int c_req) {
     cudaFree(table);
     return set_cuda_error(ctx, e, "cudaMalloc(window table scratch)");
   }
-  e = cudaMemcpyAsync(table, bases->dev, n * 64, cudaMemcpyDeviceToDevice, ctx->stream);
+  e = cudaMemcpyAsync(table, points, n * 64, cudaMemcpyDeviceToDevice, ctx->stream);
   for (size_t first = 0; first < n && e == cudaSuccess; first += chunk) {
     const size_t count = first + chunk <= n ? chunk : n - first;
     msm_precompute_kernel<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(table, n, first, count, tsh, tmp, table);
@@ -693,10 +675,52 @@ int msm_precompute_run(b200zk_ctx* ctx, b200zk_bases* bases, int c_req) {
     cudaFree(table);
     return set_cuda_error(ctx, e, "msm_precompute_kernel");
   }
+  *table_out = table;
+  memcpy(wstart_out, tsh.wstart, sizeof(tsh.wstart));
+  *c_out = tsh.c;
+  return B200ZK_OK;
+}
+
+int msm_precompute_run(b200zk_ctx* ctx, b200zk_bases* bases, int c_req) {
+  if (!bases || !bases->dev) return B200ZK_ERR_BAD_ARG;
+  if (bases->table) return B200ZK_OK;
+  const size_t n = bases->n;
+  if (n == 0) return B200ZK_OK;
+  unsigned lg = 0;
+  while (((size_t)1 << (lg + 1)) <= n) lg++;
+  // number of windows from the size (or from a requested maximum width c_req)
+  unsigned W;
+  if (c_req) W = (255 + (unsigned)c_req - 1) / (unsigned)c_req;
+  else if (lg >= 23) W = 12;   // widths 22,22,22,21 x9  -> 2^21 buckets
+  else if (lg >= 19) W = 13;   // widths 20 x8, 19 x5     -> 2^19 buckets
+  else if (lg >= 15) W = 15;   // widths 17 x15           -> 2^16 buckets
+  else if (lg >= 14) W = 16;   // widths 16 x15, 15       -> 2^15 buckets
+  else if (lg >= 13) W = 17;   // widths 15 x17           -> 2^14 buckets
+  else if (lg >= 11) W = 20;   // widths 13 x15, 12 x5    -> 2^12 buckets (mostly served by the small path)
+  else W = SMALL_TABLE_W;      // widths 6               -> the small path multiplies by 6-bit digits: its latency is
+                               //                           the double-and-add chain, the table is tiny anyway
+  // (measured per size with scripts/table_window_sweep.py: below 2^19 points the bucket count decides the latency —
+  //  too few buckets leave the accumulation with a handful of long serial runs, too many make the reduction dominate)
+  if (W > MAX_WINDOWS) W = MAX_WINDOWS;
+  void* table = nullptr;
+  uint8_t wstart[65];
+  unsigned c = 0;
+  B200ZK_TRY(build_window_table(ctx, bases->dev, n, W, &table, wstart, &c));
+  // A large SRS serving a small circuit (the reference's default: 10^6 points, tens of rows): the head of the bases
+  // also gets the narrow-window table of the small path, whose latency is the width of the digit.
+  if (!c_req && n > SMALL_TABLE_N) {
+    void* st = nullptr;
+    unsigned sc = 0;
+    if (build_window_table(ctx, bases->dev, SMALL_TABLE_N, SMALL_TABLE_W, &st, bases->small_wstart, &sc) == B200ZK_OK) {
+      bases->small_table = st;
+      bases->small_n = SMALL_TABLE_N;
+      bases->small_c = sc;
+    }
+  }
   bases->table = table;
   bases->tab_c = c;
   bases->tab_W = W;
-  memcpy(bases->tab_wstart, tsh.wstart, sizeof(tsh.wstart));
+  memcpy(bases->tab_wstart, wstart, sizeof(wstart));
   return B200ZK_OK;
 }
 
@@ -725,17 +749,19 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
   memset(&sh, 0, sizeof(sh));
   if (bases->table && !ctx->forced_window && !ctx->msm_no_tiny && n * (size_t)bases->tab_W <= TINY_MAX_TERMS) {
     // small problem: one thread per (point, window) term of the table, two launches
-    sh.c = bases->tab_c;
-    sh.W = bases->tab_W;
-    sh.tab_stride = (unsigned)bases->n;
+    const bool head = bases->small_table && first_base + n <= bases->small_n;  // narrow windows: shorter digit chains
+    const void* tiny_table = head ? bases->small_table : bases->table;
+    sh.c = head ? bases->small_c : bases->tab_c;
+    sh.W = head ? SMALL_TABLE_W : bases->tab_W;
+    sh.tab_stride = (unsigned)(head ? bases->small_n : bases->n);
     sh.first = (unsigned)first_base;
-    memcpy(sh.wstart, bases->tab_wstart, sizeof(sh.wstart));
+    memcpy(sh.wstart, head ? bases->small_wstart : bases->tab_wstart, sizeof(sh.wstart));
     const unsigned terms = (unsigned)(n * sh.W);
     const unsigned blocks = (terms + BIG_THREADS - 1) / BIG_THREADS;
     B200ZK_TRY(ensure(ctx, ws.msm_big, (size_t)blocks * 128, st));
     const size_t shm = (size_t)BIG_THREADS * sizeof(G1XYZZ);
     PhaseTimer pt(ctx, PH_MSM_ACCUMULATE, st);
-    msm_tiny_kernel<<<blocks, BIG_THREADS, shm, st>>>(bases->table, (const uint4*)scalars_dev, (unsigned)n, sh, ws.msm_big.p);
+    msm_tiny_kernel<<<blocks, BIG_THREADS, shm, st>>>(tiny_table, (const uint4*)scalars_dev, (unsigned)n, sh, ws.msm_big.p);
     B200ZK_LAUNCH_CHECK(ctx, "msm_tiny_kernel");
     msm_tiny_final_kernel<<<1, BIG_THREADS, shm, st>>>(ws.msm_big.p, blocks, out_dev, out_kind);
     B200ZK_LAUNCH_CHECK(ctx, "msm_tiny_final_kernel");

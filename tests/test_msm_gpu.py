@@ -434,3 +434,27 @@ def test_pseudo_random_bases(ctx):
                 assert zk.MultiExp(srs, sc) == cref.msm(pts, sc, n, nthreads=cref.ncores())
     finally:
         srs.close()
+
+
+def test_small_msm_on_the_head_of_a_large_table(ctx):
+    """the reference's default: a large SRS (here 2^15 points) serving tiny commitments — the head of the bases has a
+    narrow-window table of its own; results equal the oracle for sizes on both sides of its 2048-point limit and for a
+    sub-range that straddles it"""
+    import torch
+
+    n = 1 << 15
+    pts = structured(n)
+    sc = cref.random_fr(n, 0xB2000001 + 77)
+    srs = zk.SRS(pts, ctx).precompute()
+    try:
+        for m in (1, 11, 67, 2048, 2049, 5000):
+            assert zk.MultiExp(srs, sc[: m * 32], n=m) == cref.msm(pts, sc, m, nthreads=4), m
+        d = torch.from_numpy(sc.copy()).cuda()
+        out = torch.zeros(64, dtype=torch.uint8, device="cuda")
+        for first, m in ((100, 50), (2000, 100), (3000, 10)):
+            zk.MultiExp(srs, d[first * 32:(first + m) * 32], n=m, first_base=first, out=out)
+            ctx.sync()
+            want = cref.msm(pts[first * 64:(first + m) * 64], sc[first * 32:(first + m) * 32], m, nthreads=2)
+            assert out.cpu().numpy().tobytes() == want, (first, m)
+    finally:
+        srs.close()
