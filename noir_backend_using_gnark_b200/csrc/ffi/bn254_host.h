@@ -492,10 +492,19 @@ inline F12 line_value(const Fp2& m, const G2& r, const G1& p) {
   l.c[3] = fp_sub(c3.a0, fp_mul(c3.a1, c9)); l.c[9] = c3.a1;
   return l;
 }
+// The slopes of the Miller loop and the constant terms of its lines depend on Q only: a G2Prepared holds them per step
+// (already in the Fp[w] basis), so that later pairings against the same Q do no G2 arithmetic and no inversion.
+struct G2Prepared {
+  struct Line { Fe4 m_lo, m_hi, c_lo, c_hi; };  // line(P) = -yP + (m_lo + m_hi w^6) xP w + (c_lo + c_hi w^6) w^3
+  std::vector<Line> lines;
+  bool usable = false;  // false: Q at infinity or a degenerate (vertical) step -> use the generic loop
+};
 // f <- f * line(R, S)(P), R <- R + S  (S == R doubles).  A vertical line contributes xP - xR' w^2.
-inline void miller_step(F12& f, G2& r, const G2& s, const G1& p) {
+// rec != null: the step's line is appended to it (or it is marked unusable on a degenerate step).
+inline void miller_step(F12& f, G2& r, const G2& s, const G1& p, G2Prepared* rec = nullptr) {
   if (r.inf || s.inf) {
     if (r.inf) r = s;
+    if (rec) rec->usable = false;
     return;
   }
   Fp2 m;
@@ -508,6 +517,7 @@ inline void miller_step(F12& f, G2& r, const G2& s, const G1& p) {
       l.c[8] = fp_neg(r.x.a1);
       f = f12_mul(l, f);
       r.inf = true;
+      if (rec) rec->usable = false;
       return;
     }
     const Fp2 xx = f2_mul(r.x, r.x);
@@ -516,6 +526,16 @@ inline void miller_step(F12& f, G2& r, const G2& s, const G1& p) {
     m = f2_mul(f2_sub(s.y, r.y), f2_inv(f2_sub(s.x, r.x)));
   }
   f = f12_mul(line_value(m, r, p), f);  // sparse operand first: f12_mul skips its zero coefficients
+  if (rec) {
+    const Fe4 c9 = fp_small(9);
+    const Fp2 c3 = f2_sub(r.y, f2_mul(m, r.x));
+    G2Prepared::Line l;
+    l.m_lo = fp_sub(m.a0, fp_mul(m.a1, c9));
+    l.m_hi = m.a1;
+    l.c_lo = fp_sub(c3.a0, fp_mul(c3.a1, c9));
+    l.c_hi = c3.a1;
+    rec->lines.push_back(l);
+  }
   G2 n;
   n.x = f2_sub(f2_sub(f2_mul(m, m), r.x), s.x);
   n.y = f2_sub(f2_mul(m, f2_sub(r.x, n.x)), r.y);
@@ -524,14 +544,24 @@ inline void miller_step(F12& f, G2& r, const G2& s, const G1& p) {
 }
 // prod_i f_{6x+2,Q_i}(P_i) with the line corrections of the optimal ate pairing; the squaring of the accumulator is
 // shared by all pairs
-inline F12 miller_loop_product(const std::vector<std::pair<G1, G2>>& pairs) {
+// record != null (one entry per pair): the lines of every Q are recorded on the way, at no extra G2 work
+inline F12 miller_loop_product(const std::vector<std::pair<G1, G2>>& pairs, G2Prepared* record = nullptr) {
   std::vector<const G1*> ps;
   std::vector<const G2*> qs;
-  for (const auto& pq : pairs)
+  std::vector<G2Prepared*> recs;
+  for (size_t k = 0; k < pairs.size(); k++) {
+    const auto& pq = pairs[k];
+    if (record) {
+      record[k].lines.clear();
+      record[k].usable = false;
+    }
     if (!pq.first.inf && !pq.second.inf) {
       ps.push_back(&pq.first);
       qs.push_back(&pq.second);
+      recs.push_back(record ? &record[k] : nullptr);
+      if (record) record[k].usable = true;
     }
+  }
   F12 f = f12_one();
   std::vector<G2> r;
   for (auto q : qs) r.push_back(*q);
@@ -539,8 +569,8 @@ inline F12 miller_loop_product(const std::vector<std::pair<G1, G2>>& pairs) {
   for (int i = 63; i >= 0; i--) {
     f = f12_sqr(f);
     for (size_t k = 0; k < r.size(); k++) {
-      miller_step(f, r[k], r[k], *ps[k]);
-      if ((ATE_LOOP_LO >> i) & 1) miller_step(f, r[k], *qs[k], *ps[k]);
+      miller_step(f, r[k], r[k], *ps[k], recs[k]);
+      if ((ATE_LOOP_LO >> i) & 1) miller_step(f, r[k], *qs[k], *ps[k], recs[k]);
     }
   }
   const FrobTable& T = frob_table();
@@ -553,12 +583,51 @@ inline F12 miller_loop_product(const std::vector<std::pair<G1, G2>>& pairs) {
     nq2.x = f2_mul(f2_conj(q1.x), T.twist_x);
     nq2.y = f2_neg(f2_mul(f2_conj(q1.y), T.twist_y));
     nq2.inf = false;
-    miller_step(f, r[k], q1, *ps[k]);
-    miller_step(f, r[k], nq2, *ps[k]);
+    miller_step(f, r[k], q1, *ps[k], recs[k]);
+    miller_step(f, r[k], nq2, *ps[k], recs[k]);
   }
   return f;
 }
 inline F12 miller_loop(const G2& q, const G1& p) { return miller_loop_product({{p, q}}); }
+// ---- fixed second argument: the verifier always pairs against the two G2 elements of the SRS
+inline G2Prepared g2_prepare(const G2& q) {  // stand-alone preparation: a Miller loop against the generator, recorded
+  G2Prepared out;
+  if (q.inf) return out;
+  miller_loop_product({{g1_generator(), q}}, &out);
+  return out;
+}
+// prod_i f_{6x+2,Q_i}(P_i) for prepared Q_i (same value as miller_loop_product)
+inline F12 miller_loop_prepared(const std::vector<std::pair<G1, const G2Prepared*>>& pairs) {
+  std::vector<std::pair<G1, const G2Prepared*>> act;
+  for (const auto& pq : pairs)
+    if (!pq.first.inf) act.push_back(pq);
+  F12 f = f12_one();
+  std::vector<size_t> pos(act.size(), 0);
+  auto apply = [&](size_t k) {
+    const G2Prepared::Line& ln = act[k].second->lines[pos[k]++];
+    const G1& p = act[k].first;
+    F12 l = f12_zero();
+    l.c[0] = fp_neg(p.y);
+    l.c[1] = fp_mul(ln.m_lo, p.x);
+    l.c[7] = fp_mul(ln.m_hi, p.x);
+    l.c[3] = ln.c_lo;
+    l.c[9] = ln.c_hi;
+    f = f12_mul(l, f);
+  };
+  for (int i = 63; i >= 0; i--) {
+    f = f12_sqr(f);
+    for (size_t k = 0; k < act.size(); k++) {
+      apply(k);
+      if ((ATE_LOOP_LO >> i) & 1) apply(k);
+    }
+  }
+  for (size_t k = 0; k < act.size(); k++) {
+    apply(k);
+    apply(k);
+  }
+  return f;
+}
+
 // f^((p^12 - 1) / r) = ((f^(p^6 - 1))^(p^2 + 1))^((p^4 - p^2 + 1) / r); the last exponent is exactly
 // p^3 + (6x^2 + 1) p^2 - (36x^3 + 18x^2 + 12x - 1) p - (36x^3 + 30x^2 + 18x + 2) for the BN parameter x
 inline F12 final_exponentiation(const F12& f) {
@@ -617,8 +686,13 @@ inline F12 final_exponentiation(const F12& f) {
   return f12_mul(acc, g3);
 }
 // prod_i e(P_i, Q_i) == 1
-inline bool pairing_product_is_one(const std::vector<std::pair<G1, G2>>& pairs) {
-  return f12_eq(final_exponentiation(miller_loop_product(pairs)), f12_one());
+inline bool pairing_product_is_one(const std::vector<std::pair<G1, G2>>& pairs, G2Prepared* record = nullptr) {
+  return f12_eq(final_exponentiation(miller_loop_product(pairs, record)), f12_one());
+}
+
+// the same test against prepared second arguments
+inline bool pairing_product_is_one_prepared(const std::vector<std::pair<G1, const G2Prepared*>>& pairs) {
+  return f12_eq(final_exponentiation(miller_loop_prepared(pairs)), f12_one());
 }
 
 }  // namespace ffi

@@ -70,6 +70,7 @@ struct State {
   b200zk_bases* bases = nullptr;
   size_t srs_n = 0;
   G2 g2[2];
+  G2Prepared g2_prepared[2];  // Miller-loop lines of the two SRS elements (every verification pairs against them)
   std::vector<uint8_t> srs_file;  // u32 count || compressed G1 powers, until they are uploaded
   bool srs_ready = false, bases_ready = false;
   // Parsed circuits and device-resident keys, found again by the digest of the ACIR text (the reference re-parses the
@@ -375,7 +376,7 @@ struct Transcript {
 //   e(C_i - v_i G1 + z_i H_i, G2) * e(-H_i, alpha G2) == 1
 // are folded with a challenge lambda derived from everything they depend on, so one product of two pairings decides:
 //   e(sum_i lambda^i (C_i + z_i H_i) - (sum_i lambda^i v_i) G1, G2) * e(-sum_i lambda^i H_i, alpha G2) == 1
-bool kzg_verify_two(const G1 C[2], const Fe4 z[2], const Fe4 v[2], const G1 Hq[2], const G2 g2[2]) {
+bool kzg_verify_two(const G1 C[2], const Fe4 z[2], const Fe4 v[2], const G1 Hq[2], const G2 g2[2], G2Prepared* prepared) {
   Transcript t;
   t.begin("lambda");
   for (int i = 0; i < 2; i++) {
@@ -391,10 +392,15 @@ bool kzg_verify_two(const G1 C[2], const Fe4 z[2], const Fe4 v[2], const G1 Hq[2
   lhs = g1j_add_affine(lhs, C[0]);
   G1J hs = g1_msm_small({Hq[1]}, {lambda});
   hs = g1j_add_affine(hs, Hq[0]);
-  return pairing_product_is_one({{g1j_to_affine(lhs), g2[0]}, {g1_neg(g1j_to_affine(hs)), g2[1]}});
+  const G1 a = g1j_to_affine(lhs), b = g1_neg(g1j_to_affine(hs));
+  if (prepared && prepared[0].usable && prepared[1].usable)
+    return pairing_product_is_one_prepared({{a, &prepared[0]}, {b, &prepared[1]}});
+  // first verification of the process: the generic loop, which records the lines of the two SRS elements on the way
+  return pairing_product_is_one({{a, g2[0]}, {b, g2[1]}}, prepared);
 }
 
-bool plonk_verify(const ParsedProof& pr, const ParsedVk& vk, const std::vector<Fe4>& pub, const G2 g2[2]) {  // plonk.Verify
+bool plonk_verify(const ParsedProof& pr, const ParsedVk& vk, const std::vector<Fe4>& pub, const G2 g2[2],
+                  G2Prepared* prepared) {  // plonk.Verify
   auto M = [](const Fe4& a, const Fe4& b) { return host::mul(HFR, a, b); };
   auto A = [](const Fe4& a, const Fe4& b) { return host::add(HFR, a, b); };
   auto S = [](const Fe4& a, const Fe4& b) { return host::sub(HFR, a, b); };
@@ -467,7 +473,7 @@ bool plonk_verify(const ParsedProof& pr, const ParsedVk& vk, const std::vector<F
   const G1 Cs[2] = {g1j_to_affine(g1j_add_affine(g1_msm_small(dpts, dsc), digests[0])), pr.Z};
   const Fe4 zs[2] = {zeta, M(zeta, vk.generator)}, vs[2] = {fe, zu};
   const G1 Hs[2] = {pr.batched_H, pr.zshift_H};
-  return kzg_verify_two(Cs, zs, vs, Hs, g2);
+  return kzg_verify_two(Cs, zs, vs, Hs, g2, prepared);
 }
 
 // hex text written straight into the malloc'ed result (the pk of a 2^20-row circuit is 650 MB of hex)
@@ -713,7 +719,7 @@ uint8_t PlonkVerifyWithVK(GoString acirJSON, GoString encodedProof, GoString enc
   }
   trace("circuit read / found");
   ensure_srs();  // vk.InitKZG(srs): the G2 elements live in the SRS file
-  const bool ok = plonk_verify(proof, vk, pub, state().g2);
+  const bool ok = plonk_verify(proof, vk, pub, state().g2, state().g2_prepared);
   trace("plonk.Verify (host pairing)");
   return ok ? 1 : 0;
 }

@@ -24,6 +24,11 @@ int main(int argc, char** argv) {
   const G1 p = g1_mul(g1_generator(), a);
   const G2 q = g2_mul(g2_generator(), b);
   const F12 ml = miller_loop(q, p);
+  const G2Prepared prep = g2_prepare(q);
+  if (!prep.usable || !f12_eq(miller_loop_prepared({{p, &prep}}), ml)) {  // fixed-argument variant: same value
+    printf("prepared Miller loop differs\n");
+    return 1;
+  }
   print_f12(ml);
   print_f12(final_exponentiation(ml));
   const Fe4 ab = host::mul(HFR, a, b);
@@ -31,6 +36,13 @@ int main(int argc, char** argv) {
   const bool ok = pairing_product_is_one({{p, q}, {g1_neg(g1_mul(g1_generator(), ab)), g2_generator()}});
   auto t1 = std::chrono::steady_clock::now();
   const bool bad = pairing_product_is_one({{p, q}, {g1_neg(g1_mul(g1_generator(), host::add(HFR, ab, HFR.one))), g2_generator()}});
+  const G2Prepared pg = g2_prepare(g2_generator());
+  const bool okp = pairing_product_is_one_prepared({{p, &prep}, {g1_neg(g1_mul(g1_generator(), ab)), &pg}});
+  const bool badp = pairing_product_is_one_prepared({{p, &prep}, {g1_neg(g1_mul(g1_generator(), host::add(HFR, ab, HFR.one))), &pg}});
+  if (okp != ok || badp != bad) {
+    printf("prepared product check differs\n");
+    return 1;
+  }
   printf("%d %d %.2f\n", ok ? 1 : 0, bad ? 1 : 0, std::chrono::duration<double, std::milli>(t1 - t0).count());
   return 0;
 }
