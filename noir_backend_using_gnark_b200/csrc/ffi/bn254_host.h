@@ -654,59 +654,34 @@ inline F12 miller_loop_prepared(const std::vector<std::pair<G1, const G2Prepared
 // f^((p^12 - 1) / r) = ((f^(p^6 - 1))^(p^2 + 1))^((p^4 - p^2 + 1) / r); the last exponent is exactly
 // p^3 + (6x^2 + 1) p^2 - (36x^3 + 18x^2 + 12x - 1) p - (36x^3 + 30x^2 + 18x + 2) for the BN parameter x
 inline F12 final_exponentiation(const F12& f) {
+  // easy part: g = f^((p^6 - 1)(p^2 + 1)) lies in the cyclotomic subgroup, where inversion is the p^6-Frobenius
   F12 g = f12_mul(f12_conj6(f), f12_inv(f));
   g = f12_mul(f12_frobenius(f12_frobenius(g)), g);
-  const F12 g1 = f12_frobenius(g), g2 = f12_frobenius(g1), g3 = f12_frobenius(g2);
-  typedef unsigned __int128 u128;
-  const u128 x = 4965661367192848881ULL;
-  // x^2 < 2^126 fits u128; x^3 < 2^189 needs three limbs: compute with schoolbook on 64-bit limbs
-  auto mul_small = [](const uint64_t a[3], uint64_t k, uint64_t out[3]) {
-    u128 c = 0;
-    for (int i = 0; i < 3; i++) {
-      c += (u128)a[i] * k;
-      out[i] = (uint64_t)c;
-      c >>= 64;
+  // hard part through the powers A = g^x, B = g^(x^2), C = g^(x^3) of the BN parameter (63 bits, weight 28):
+  //   g^(6x^2+1)            = B^6 g
+  //   g^(36x^3+18x^2+12x-1) = (C^2 B)^18 A^12 / g
+  //   g^(36x^3+30x^2+18x+2) = (C^2 B)^18 B^12 A^18 g^2
+  auto pow_x = [](const F12& a) {
+    const uint64_t x = 4965661367192848881ULL;
+    F12 r = a;
+    for (int bit = 61; bit >= 0; bit--) {
+      r = f12_sqr(r);
+      if ((x >> bit) & 1) r = f12_mul(r, a);
     }
+    return r;
   };
-  auto add3 = [](const uint64_t a[3], const uint64_t b[3], uint64_t out[3]) {
-    u128 c = 0;
-    for (int i = 0; i < 3; i++) {
-      c += (u128)a[i] + b[i];
-      out[i] = (uint64_t)c;
-      c >>= 64;
-    }
-  };
-  const u128 x2 = x * x;
-  uint64_t X1[3] = {(uint64_t)x, 0, 0}, X2[3] = {(uint64_t)x2, (uint64_t)(x2 >> 64), 0}, X3[3];
-  mul_small(X2, (uint64_t)x, X3);
-  uint64_t t[3], u[3], e0[3], e1[3], e2[3];
-  // e2 = 6x^2 + 1
-  mul_small(X2, 6, e2);
-  { uint64_t one[3] = {1, 0, 0}; add3(e2, one, e2); }
-  // e1 = 36x^3 + 18x^2 + 12x - 1
-  mul_small(X3, 36, t); mul_small(X2, 18, u); add3(t, u, e1); mul_small(X1, 12, u); add3(e1, u, e1);
-  for (int i = 0; i < 3; i++)
-    if (e1[i]-- != 0) break;  // minus one, with borrow
-  // e0 = 36x^3 + 30x^2 + 18x + 2
-  mul_small(X2, 30, u); add3(t, u, e0); mul_small(X1, 18, u); add3(e0, u, e0);
-  { uint64_t two[3] = {2, 0, 0}; add3(e0, two, e0); }
-  // simultaneous exponentiation: g2^e2 * conj(g1)^e1 * conj(g)^e0, then times g3
-  F12 base[3] = {f12_conj6(g), f12_conj6(g1), g2};
-  const uint64_t* ex[3] = {e0, e1, e2};
-  F12 table[8];
-  table[0] = f12_one();
-  for (int m = 1; m < 8; m++) {
-    const int low = m & -m, idx = low == 1 ? 0 : low == 2 ? 1 : 2;
-    table[m] = (m == low) ? base[idx] : f12_mul(table[m ^ low], base[idx]);
-  }
-  F12 acc = f12_one();
-  for (int bit = 191; bit >= 0; bit--) {
-    acc = f12_sqr(acc);
-    int m = 0;
-    for (int k = 0; k < 3; k++) m |= (int)((ex[k][bit / 64] >> (bit % 64)) & 1) << k;
-    if (m) acc = f12_mul(acc, table[m]);
-  }
-  return f12_mul(acc, g3);
+  const F12 A = pow_x(g), B = pow_x(A), C = pow_x(B);
+  const F12 B3 = f12_mul(f12_sqr(B), B), B6 = f12_sqr(B3), B12 = f12_sqr(B6);
+  const F12 T = f12_mul(f12_sqr(C), B);
+  const F12 T2 = f12_sqr(T), T16 = f12_sqr(f12_sqr(f12_sqr(T2))), T18 = f12_mul(T16, T2);
+  const F12 A3 = f12_mul(f12_sqr(A), A), A6 = f12_sqr(A3), A12 = f12_sqr(A6), A18 = f12_mul(A12, A6);
+  const F12 m2 = f12_mul(B6, g);                                              // g^lambda2
+  const F12 m1 = f12_mul(f12_mul(T18, A12), f12_conj6(g));                    // g^-lambda1
+  const F12 m0 = f12_mul(f12_mul(T18, B12), f12_mul(A18, f12_sqr(g)));        // g^-lambda0
+  const F12 g3 = f12_frobenius(f12_frobenius(f12_frobenius(g)));
+  F12 r = f12_mul(f12_conj6(m0), f12_frobenius(f12_conj6(m1)));
+  r = f12_mul(r, f12_frobenius(f12_frobenius(m2)));
+  return f12_mul(r, g3);
 }
 // prod_i e(P_i, Q_i) == 1
 inline bool pairing_product_is_one(const std::vector<std::pair<G1, G2>>& pairs, G2Prepared* record = nullptr) {
