@@ -25,6 +25,17 @@ def test_strerror_and_null_handling(lib_built):
     assert lib.b200zk_launch_count(None) == 0
     lib.b200zk_destroy(None)
     lib.b200zk_bases_free(None, None)
+    # every later addition to the ABI refuses null handles the same way
+    assert lib.b200zk_plonk_prove_hex(None, None, None, 0, None, None) == -3
+    assert lib.b200zk_plonk_set_solution_map(None, None, None, 0) == -3
+    assert lib.b200zk_plonk_set_commit_lanes(None, 3) == -3
+    assert lib.b200zk_plonk_unsatisfied_row(None) == -1
+    assert lib.b200zk_msm_windows(None, None, 0) == -3
+    assert lib.b200zk_host_alloc(None, 16, None) == -3
+    assert lib.b200zk_msm_set_reduce_chunk(None, 3) == -3
+    assert lib.b200zk_msm_set_small_path(None, 1) == -3
+    assert lib.b200zk_msm_set_host_chunks(None, 2) == -3
+    assert b"constraint" in lib.b200zk_strerror(-6)
 
 
 def test_no_cpu_fallback(lib_built):
