@@ -502,6 +502,20 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
                     "hbm_frac": gbs / hbm, "peak_source": "measured" if "hbm_gbs" in peaks else "fallback",
                     "passes": -(-nlog // 8) if nlog > 10 else 1}
         del a
+        if not args.no_cpu:
+            # CPU arm of the NTT metric on a bounded sample: the C port of fft.Domain.FFT on all host cores
+            from oracle import cref
+
+            slog = min(nlog, 22)
+            sample = random_fr_images(1 << slog, SEED_NTT)
+            cores = cref.ncores()
+            cref.ntt(sample, slog, 0, 0, 0, cores)          # builds the domain tables
+            t0 = time.perf_counter()
+            cref.ntt(sample, slog, 0, 0, 0, cores)
+            dt = time.perf_counter() - t0
+            ntt_info["cpu_baseline"] = {"value": 64.0 * (1 << slog) / dt / 1e9, "unit": "GB/s", "ms": dt * 1e3, "cores": cores,
+                                        "kind": "port", "sample": "one 2^%d DIF transform (includes copying the input), C "
+                                        "restatement of gnark-crypto fft.Domain.FFT (not gnark itself)" % slog}
 
     cpu = None
     if not args.no_cpu:
