@@ -202,6 +202,22 @@ int b200zk_plonk_pk_poly(b200zk_ctx* ctx, const b200zk_plonk_pk* pk, int which, 
 int b200zk_plonk_prove(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solution_host, const void* blinding_host,
                        void* proof_out);
 long long b200zk_plonk_unsatisfied_row(const b200zk_plonk_pk* pk);
+/* ---- the same prover over the 2, 4 or 8 GPUs of one box (one process / context / key per GPU, SPMD) -------
+ * Every rank runs b200zk_plonk_setup on its own GPU (same circuit, full SRS), then the ranks map each other's key
+ * arena (b200zk_plonk_arena + b200zk_ipc_export / b200zk_ipc_import for other processes; the raw pointers for contexts
+ * of one process) and call b200zk_plonk_join with the world's arena pointers as seen from the calling process
+ * (arena_ptrs[rank] = the own arena).  From then on b200zk_plonk_prove must be called by ALL ranks: rank 0 passes the
+ * solution and the blinding (the other ranks may pass NULL: they fetch both from rank 0 over NVLink), every rank
+ * returns the same 832-byte proof.  What is sharded (BASELINE.json north_star): every commitment's MSM by point range
+ * (partials combined through peer loads), the five coset transforms of the 4n domain and the inverse one as four-step
+ * NTTs whose transpose rides on the last butterfly pass as NVLink peer stores, and the quotient kernel by index range;
+ * the n-sized stages are replicated.  There is no collective library on the data path: barriers are epoch counters in
+ * the mapped arenas (a rank that does not arrive within 20 s fails the proof instead of hanging the device).
+ * Circuits need log2n_big == log2n + 2 and at least 4 * world columns per rank (any circuit worth sharding).
+ * b200zk_plonk_leave returns the key to single-GPU proving (call it on every rank before freeing a key). */
+int b200zk_plonk_arena(b200zk_ctx* ctx, const b200zk_plonk_pk* pk, void** base_dev, size_t* bytes);
+int b200zk_plonk_join(b200zk_ctx* ctx, b200zk_plonk_pk* pk, unsigned rank, unsigned world, void* const* arena_ptrs);
+int b200zk_plonk_leave(b200zk_ctx* ctx, b200zk_plonk_pk* pk);
 /* tests / tuning: the independent commitments of one prover round (L,R,O; H1,H2,H3; the 8 of Setup) run on 3 MSM lanes
  * of the context (own stream and workspace each) so that the latency-bound phases of one MSM hide under the bucket
  * accumulation of another; 1 = one after the other.  Results do not depend on it. */

@@ -97,6 +97,9 @@ def load() -> C.CDLL:
         "b200zk_plonk_pk_poly": (i, [vp, vp, i, vp]),
         "b200zk_plonk_prove": (i, [vp, vp, vp, vp, vp]),
         "b200zk_plonk_unsatisfied_row": (C.c_longlong, [vp]),
+        "b200zk_plonk_arena": (i, [vp, vp, C.POINTER(vp), C.POINTER(sz)]),
+        "b200zk_plonk_join": (i, [vp, vp, u, u, C.POINTER(vp)]),
+        "b200zk_plonk_leave": (i, [vp, vp]),
         "b200zk_plonk_set_commit_lanes": (i, [vp, i]),
         "b200zk_plonk_set_solution_map": (i, [vp, vp, vp, sz]),
         "b200zk_plonk_prove_hex": (i, [vp, vp, vp, sz, vp, vp]),

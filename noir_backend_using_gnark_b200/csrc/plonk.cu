@@ -267,6 +267,12 @@ struct QuotientArgs {
   const uint4* tw_big;  // w_{4n}^i, i < N4/2
   uint4* out;
   unsigned log_big, log_ratio;
+  // multi-GPU: this launch covers the contiguous range [base, base + count) of the bit-reversed coset evaluations; every
+  // array above is indexed by i - base.  z(wX) of a position may live in the range of the rank whose id differs in the
+  // lowest bit (8 ranks, 4n domain): ez_other holds that rank's range of ez.
+  size_t base, count;
+  unsigned log_local;
+  const uint4* ez_other;
   FrArg alpha, beta, gamma, beta_u, beta_uu;
   FrArg xn_inv[8];
 };
@@ -274,11 +280,15 @@ struct QuotientArgs {
 __global__ void __launch_bounds__(256) k_quotient(QuotientArgs q) {
   const size_t N = (size_t)1 << q.log_big;
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i >= N) return;
-  const size_t nat = (size_t)(__brev((unsigned)i) >> (32 - q.log_big));
+  if (i >= q.count) return;
+  const size_t gi = q.base + i;  // position in the full bit-reversed vector
+  const size_t nat = (size_t)(__brev((unsigned)gi) >> (32 - q.log_big));
   const size_t ratio = (size_t)1 << q.log_ratio;
   const size_t nat_s = (nat + ratio) & (N - 1);
-  const size_t ishift = (size_t)(__brev((unsigned)nat_s) >> (32 - q.log_big));
+  const size_t gshift = (size_t)(__brev((unsigned)nat_s) >> (32 - q.log_big));
+  const size_t lmask = ((size_t)1 << q.log_local) - 1;
+  const uint4* ez_s = (gshift >> q.log_local) == (q.base >> q.log_local) ? q.ez : q.ez_other;
+  const size_t ishift = gshift & lmask;
   const Fr alpha = arg(q.alpha), beta = arg(q.beta), gamma = arg(q.gamma);
   const Fr L = fe_load_ro<FrParams>(q.el + 2 * i), R = fe_load_ro<FrParams>(q.er + 2 * i),
            O = fe_load_ro<FrParams>(q.eo + 2 * i);
@@ -299,7 +309,7 @@ __global__ void __launch_bounds__(256) k_quotient(QuotientArgs q) {
   Fr b = fe_add(Lg, fe_mul(beta, fe_load_ro<FrParams>(q.s1 + 2 * i)));
   b = fe_mul(b, fe_add(Rg, fe_mul(beta, fe_load_ro<FrParams>(q.s2 + 2 * i))));
   b = fe_mul(b, fe_add(Og, fe_mul(beta, fe_load_ro<FrParams>(q.s3 + 2 * i))));
-  b = fe_mul(b, fe_load_ro<FrParams>(q.ez + 2 * ishift));
+  b = fe_mul(b, fe_load_ro<FrParams>(ez_s + 2 * ishift));
   const Fr perm = fe_sub(b, a);
   // (z - 1) * L1
   const Fr one_term = fe_mul(fe_sub(z, fe_one<FrParams>()), fe_load_ro<FrParams>(q.lone + 2 * i));
@@ -467,6 +477,74 @@ __global__ void __launch_bounds__(256) k_fold7(FoldArgs a) {
   fe_store(a.out + 2 * j, v);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// multi-GPU prover (b200zk_plonk_join): the ranks' arenas are mapped into each other (CUDA IPC / same process), so a
+// buffer of rank k is `base[k] + offset` with the SAME offset on every rank.  No collective library on the data path:
+// barriers are epoch counters written into the peers' arenas, data moves by peer stores (NTT exchange, fused into the
+// butterfly pass), peer loads (partial commitments) and peer DMA copies (polynomials).
+// ---------------------------------------------------------------------------------------------------
+struct PeerSet {
+  unsigned world, rank;
+  char* base[8];
+};
+
+// Stream-ordered barrier: thread t publishes `epoch` in slot [rank] of peer t's flag array, then waits until slot [t]
+// of the own array has reached it.  Epochs only grow, so a peer that is already one barrier ahead also satisfies the
+// wait.  A peer that never arrives (crashed process) raises *err after 20 s instead of hanging the device.
+__global__ void k_group_barrier(PeerSet ps, size_t flags_off, size_t err_off, unsigned epoch) {
+  const unsigned t = threadIdx.x;
+  if (t >= ps.world) return;
+  __threadfence_system();
+  unsigned* remote = reinterpret_cast<unsigned*>(ps.base[t] + flags_off) + ps.rank;
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
+  const unsigned* mine = reinterpret_cast<const unsigned*>(ps.base[ps.rank] + flags_off) + t;
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+    if ((int)(v - epoch) >= 0) break;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 20000000000ull) {
+      *reinterpret_cast<unsigned*>(ps.base[ps.rank] + err_off) = 1u;
+      break;
+    }
+    __nanosleep(100);
+  }
+}
+
+// commitment = canonical affine of the sum over ranks of the extended-Jacobian partials of one slot (block b: slot[b]);
+// every rank reads all partials through the peer mappings and forms the same point
+struct SumSlots {
+  int slot[8];
+};
+__global__ void k_sum_partials_peers(PeerSet ps, size_t gather_off, SumSlots sl, void* points) {
+  if (threadIdx.x != 0) return;
+  const int slot = sl.slot[blockIdx.x];
+  G1XYZZ total = g1_xyzz_inf();
+  for (unsigned k = 0; k < ps.world; k++) {
+    G1XYZZ q = g1_load_xyzz(ps.base[k] + gather_off, slot);
+    g1_add(total, q);
+  }
+  g1_store_affine(points, slot, g1_to_affine_single(total));
+}
+
+// column-block shard of the zero-padded coefficient vector: S[r][c_lo] = poly[r*C + rank*C_loc + c_lo] (0 beyond len)
+__global__ void k_build_colblock(const uint4* __restrict__ poly, size_t len, uint4* __restrict__ shard, unsigned log2c,
+                                 unsigned cl, unsigned rank, size_t count) {
+  size_t l = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (l >= count) return;
+  const size_t r = l >> cl, c = l & (((size_t)1 << cl) - 1);
+  const size_t g = (r << log2c) | ((size_t)rank << cl) | c;
+  uint4 a = make_uint4(0, 0, 0, 0), b = a;
+  if (g < len) {
+    a = poly[2 * g];
+    b = poly[2 * g + 1];
+  }
+  shard[2 * l] = a;
+  shard[2 * l + 1] = b;
+}
+
 }  // namespace b200zk
 
 // ---------------------------------------------------------------------------------------------------
@@ -497,6 +575,14 @@ struct b200zk_plonk_pk {
   // optional replacement for the local MSM of every commitment (multi-GPU: point-range-sharded MSM + NVLink gather)
   b200zk_commit_fn commit_hook = nullptr;
   void* commit_user = nullptr;
+  // multi-GPU SPMD prover (b200zk_plonk_join): peers' arenas as seen from this process, barrier state
+  unsigned rank = 0, world = 1, log2g = 0, dist_log2c = 0;
+  size_t arena_bytes = 0;
+  char* peer_base[8] = {};
+  uint32_t* flags = nullptr;     // [world] arrival epochs written by the peers
+  uint32_t* dist_err = nullptr;  // raised by a barrier that timed out
+  void* gather = nullptr;        // 16 x 128 B: this rank's extended-Jacobian partial per commitment slot
+  unsigned epoch = 0;
 };
 
 namespace {
@@ -532,6 +618,9 @@ void carve(b200zk_plonk_pk* pk, char* base, size_t* total) {
   pk->scal = c.take<uint4>(64 * 32);
   pk->bad_row = c.take<uint32_t>(256);
   pk->points = c.take<void>(24 * 64);  // 16 result slots + device copy of the 8 vk points
+  pk->flags = c.take<uint32_t>(256);
+  pk->dist_err = c.take<uint32_t>(256);
+  pk->gather = c.take<void>(16 * 128);
   *total = c.off;
 }
 
@@ -551,8 +640,100 @@ int to_coset(b200zk_ctx* ctx, const uint4* canonical, size_t len, uint4* out, un
   return ntt_run(ctx, out, log_big, 0, B200ZK_DIF, 1);
 }
 
+// ---- multi-GPU helpers ------------------------------------------------------------------------------
+inline bool is_dist(const b200zk_plonk_pk* pk) { return pk->world > 1; }
+
+PeerSet peer_set(const b200zk_plonk_pk* pk) {
+  PeerSet ps;
+  ps.world = pk->world;
+  ps.rank = pk->rank;
+  for (int k = 0; k < 8; k++) ps.base[k] = pk->peer_base[k];
+  return ps;
+}
+
+// rank k's copy of a buffer of this rank's arena (same offset in every arena)
+template <class T>
+T* peer_ptr(const b200zk_plonk_pk* pk, unsigned k, T* local) {
+  return reinterpret_cast<T*>(pk->peer_base[k] + (reinterpret_cast<const char*>(local) - pk->arena));
+}
+
+// stream-ordered barrier over the ranks; all ranks issue their barriers in the same (program) order
+int group_barrier(b200zk_ctx* ctx, b200zk_plonk_pk* pk) {
+  pk->epoch++;
+  k_group_barrier<<<1, 32, 0, ctx->stream>>>(peer_set(pk), (size_t)((char*)pk->flags - pk->arena),
+                                             (size_t)((char*)pk->dist_err - pk->arena), pk->epoch);
+  B200ZK_LAUNCH_CHECK(ctx, "k_group_barrier");
+  return B200ZK_OK;
+}
+
+// `count` independent commitments, each sharded by point range: this rank's MSM over its range of every polynomial
+// (on the MSM lanes), one barrier, then every rank sums all ranks' partials of every slot
+int commit_dist(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const uint4* const* polys, const size_t* lens, const int* slots,
+                int count) {
+  if (count > 8) return B200ZK_ERR_BAD_ARG;
+  const bool lanes = count > 1 && !ctx->msm_single_lane;
+  if (lanes) {
+    B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    for (int l = 1; l < MSM_LANES && l < count; l++) B200ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->ws[l].stream, ctx->ev_fork, 0));
+  }
+  SumSlots sl;
+  for (int k = 0; k < 8; k++) sl.slot[k] = 0;
+  for (int k = 0; k < count; k++) {
+    const size_t lo = lens[k] * pk->rank / pk->world, hi = lens[k] * (pk->rank + 1) / pk->world;
+    sl.slot[k] = slots[k];
+    B200ZK_TRY(msm_run(ctx, pk->bases, lo, polys[k] + 2 * lo, hi - lo, (char*)pk->gather + 128 * slots[k], 1,
+                       lanes ? k % MSM_LANES : 0));
+  }
+  if (lanes)
+    for (int l = 1; l < MSM_LANES && l < count; l++) {
+      B200ZK_CUDA(ctx, cudaEventRecord(ctx->ws[l].done, ctx->ws[l].stream));
+      B200ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ws[l].done, 0));
+    }
+  B200ZK_TRY(group_barrier(ctx, pk));
+  k_sum_partials_peers<<<count, 32, 0, ctx->stream>>>(peer_set(pk), (size_t)((char*)pk->gather - pk->arena), sl, pk->points);
+  B200ZK_LAUNCH_CHECK(ctx, "k_sum_partials_peers");
+  return B200ZK_OK;
+}
+
+// buffers of the sharded 4n-domain work: the ranges [0, N4/g) of el, er, eo, ez, eqk, t hold this rank's contiguous
+// range of the bit-reversed coset evaluations; the upper halves of el / er are the two exchange buffers of the
+// four-step transforms (alternating, so one barrier per transform suffices), the upper half of eo stages the
+// column-block shard, the upper half of ez receives the neighbour rank's range of ez
+struct DistBufs {
+  size_t local;      // N4 / g elements
+  uint4 *xb[2], *stage, *ez_other;
+};
+DistBufs dist_bufs(const b200zk_plonk_pk* pk) {
+  const size_t N4 = (size_t)1 << pk->log_big;
+  DistBufs d;
+  d.local = N4 >> pk->log2g;
+  d.xb[0] = pk->el + N4;  // uint4 units: element N4/2
+  d.xb[1] = pk->er + N4;
+  d.stage = pk->eo + N4;
+  d.ez_other = pk->ez + N4;
+  return d;
+}
+
+// canonical (len coefficients) -> this rank's range of the Lagrange-coset form on the big domain (bit-reversed layout):
+// four-step DIF, first half on the column-block shard with the exchange fused into its last pass (peer stores)
+int to_coset_dist(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const uint4* canonical, size_t len, uint4* out, int seq) {
+  const DistBufs d = dist_bufs(pk);
+  const unsigned cl = pk->dist_log2c - pk->log2g;
+  k_build_colblock<<<nblocks(d.local, 256), 256, 0, ctx->stream>>>(canonical, len, d.stage, pk->dist_log2c, cl, pk->rank, d.local);
+  B200ZK_LAUNCH_CHECK(ctx, "k_build_colblock");
+  void* peers[8] = {};
+  for (unsigned k = 0; k < pk->world; k++) peers[k] = peer_ptr(pk, k, d.xb[seq & 1]);
+  B200ZK_TRY(ntt_dist_run(ctx, d.stage, d.stage, pk->log_big, pk->log2g, pk->rank, pk->dist_log2c, 0, 0, B200ZK_DIF, 1, peers));
+  B200ZK_TRY(group_barrier(ctx, pk));
+  return ntt_dist_run(ctx, d.xb[seq & 1], out, pk->log_big, pk->log2g, pk->rank, pk->dist_log2c, 1, 0, B200ZK_DIF, 1);
+}
+
 int commit(b200zk_ctx* ctx, const b200zk_plonk_pk* pk, const uint4* poly, size_t len, int slot) {
   void* out = (char*)pk->points + 64 * slot;
+  if (is_dist(pk)) {
+    const int slots[1] = {slot};
+    return commit_dist(ctx, const_cast<b200zk_plonk_pk*>(pk), &poly, &len, slots, 1);
+  }
   if (pk->commit_hook) {
     int rc = pk->commit_hook(pk->commit_user, poly, len, out);
     return rc == 0 ? B200ZK_OK : (rc < 0 ? rc : B200ZK_ERR_CUDA);
@@ -564,6 +745,7 @@ int commit(b200zk_ctx* ctx, const b200zk_plonk_pk* pk, const uint4* poly, size_t
 // phases of one MSM run under the bucket accumulation of another; everything is joined back into the context stream
 int commit_many(b200zk_ctx* ctx, const b200zk_plonk_pk* pk, const uint4* const* polys, const size_t* lens, const int* slots,
                 int count) {
+  if (is_dist(pk)) return commit_dist(ctx, const_cast<b200zk_plonk_pk*>(pk), polys, lens, slots, count);
   if (pk->commit_hook || count == 1 || ctx->msm_single_lane) {
     for (int k = 0; k < count; k++) B200ZK_TRY(commit(ctx, pk, polys[k], lens[k], slots[k]));
     return B200ZK_OK;
@@ -582,7 +764,7 @@ int commit_many(b200zk_ctx* ctx, const b200zk_plonk_pk* pk, const uint4* const* 
 // one commitment on MSM lane 1 while the context stream continues with work that neither needs its result nor
 // rewrites its input; commit_join() orders the context stream after it
 int commit_fork(b200zk_ctx* ctx, const b200zk_plonk_pk* pk, const uint4* poly, size_t len, int slot) {
-  if (pk->commit_hook || ctx->msm_single_lane) return commit(ctx, pk, poly, len, slot);
+  if (pk->commit_hook || ctx->msm_single_lane || is_dist(pk)) return commit(ctx, pk, poly, len, slot);
   B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
   B200ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->ws[1].stream, ctx->ev_fork, 0));
   B200ZK_TRY(msm_run(ctx, pk->bases, 0, poly, len, (char*)pk->points + 64 * slot, 0, 1));
@@ -698,6 +880,7 @@ int b200zk_plonk_setup(b200zk_ctx* ctx, const b200zk_bases* bases, unsigned log2
     return set_cuda_error(ctx, e, "cudaMalloc(plonk arena)");
   }
   carve(pk, pk->arena, &total);
+  pk->arena_bytes = total;
   cudaStream_t st = ctx->stream;
   auto fail = [&](int rc) {
     cudaStreamSynchronize(st);
@@ -716,6 +899,8 @@ int b200zk_plonk_setup(b200zk_ctx* ctx, const b200zk_bases* bases, unsigned log2
     if (e__ != cudaSuccess) return fail(set_cuda_error(ctx, e__, #call));     \
   } while (0)
 
+  // barrier state of the multi-GPU prover: zero BEFORE the arena can be shared with any peer
+  PK_CUDA(cudaMemsetAsync(pk->flags, 0, 512, st));
   // upload the circuit description
   const void* hsrc[5] = {ql_l, qr_l, qm_l, qo_l, qk_l};
   uint4* hdst[5] = {pk->ql, pk->qr, pk->qm, pk->qo, pk->cqk};
@@ -827,6 +1012,46 @@ int b200zk_plonk_set_commit_hook(b200zk_plonk_pk* pk, b200zk_commit_fn fn, void*
   return B200ZK_OK;
 }
 
+int b200zk_plonk_arena(b200zk_ctx* ctx, const b200zk_plonk_pk* pk, void** base_dev, size_t* bytes) {
+  if (!ctx || !pk || !base_dev || !bytes) return B200ZK_ERR_BAD_ARG;
+  *base_dev = pk->arena;
+  *bytes = pk->arena_bytes;
+  return B200ZK_OK;
+}
+
+int b200zk_plonk_join(b200zk_ctx* ctx, b200zk_plonk_pk* pk, unsigned rank, unsigned world, void* const* arena_ptrs) {
+  if (!ctx || !pk || !arena_ptrs) return B200ZK_ERR_BAD_ARG;
+  unsigned log2g = 0;
+  while ((1u << log2g) < world) log2g++;
+  if (world < 2 || world > 8 || (1u << log2g) != world || rank >= world) return B200ZK_ERR_BAD_ARG;
+  if (arena_ptrs[rank] != (void*)pk->arena) return B200ZK_ERR_BAD_ARG;
+  for (unsigned k = 0; k < world; k++)
+    if (!arena_ptrs[k]) return B200ZK_ERR_BAD_ARG;
+  // four-step shape of the big domain: C columns with at least 4 per rank, at least one row per rank
+  const unsigned logb = pk->log_big;
+  unsigned log2c = logb > 8 ? logb - 8 : 0;
+  if (log2c < log2g + 2) log2c = log2g + 2;
+  if (log2c < (logb + 1) / 2) log2c = (logb + 1) / 2;
+  if (logb < log2c + log2g || logb - pk->log2n != 2) return B200ZK_ERR_UNSUPPORTED;  // circuits below ~2^6 rows: one GPU
+  if (pk->commit_hook) return B200ZK_ERR_BAD_ARG;
+  for (unsigned k = 0; k < 8; k++) pk->peer_base[k] = k < world ? (char*)arena_ptrs[k] : nullptr;
+  pk->rank = rank;
+  pk->world = world;
+  pk->log2g = log2g;
+  pk->dist_log2c = log2c;
+  return B200ZK_OK;
+}
+
+int b200zk_plonk_leave(b200zk_ctx* ctx, b200zk_plonk_pk* pk) {
+  if (!ctx || !pk) return B200ZK_ERR_BAD_ARG;
+  B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+  B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  pk->world = 1;
+  pk->rank = 0;
+  pk->log2g = 0;
+  return B200ZK_OK;
+}
+
 int b200zk_plonk_vk(b200zk_ctx* ctx, const b200zk_plonk_pk* pk, void* out_8_points) {
   if (!ctx || !pk || !out_8_points) return B200ZK_ERR_BAD_ARG;
   memcpy(out_8_points, pk->vk_points, sizeof(pk->vk_points));
@@ -860,9 +1085,21 @@ static int prove_impl(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solution
   // the kernels below read the twiddle tables of both domains directly (identity polynomial, permutation support)
   B200ZK_TRY(ntt_prepare(ctx, log2n));
   B200ZK_TRY(ntt_prepare(ctx, logb));
+  const bool dist = is_dist(pk);
+  const DistBufs db = dist_bufs(pk);
+  if (dist && pk->rank != 0) solution_host = nullptr;  // ranks > 0 take the solution and the blinding from rank 0
   if (solution_host)
     B200ZK_CUDA(ctx, cudaMemcpyAsync(pk->sol, solution_host, (size_t)pk->nb_wires * 32, cudaMemcpyHostToDevice, st));
-  B200ZK_CUDA(ctx, cudaMemcpyAsync(pk->blinding, blinding_host, 9 * 32, cudaMemcpyHostToDevice, st));
+  if (!dist || pk->rank == 0)
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(pk->blinding, blinding_host, 9 * 32, cudaMemcpyHostToDevice, st));
+  if (dist) {
+    B200ZK_CUDA(ctx, cudaMemsetAsync(pk->dist_err, 0, 4, st));
+    B200ZK_TRY(group_barrier(ctx, pk));
+    if (pk->rank != 0) {
+      B200ZK_CUDA(ctx, cudaMemcpyAsync(pk->sol, peer_ptr(pk, 0, pk->sol), (size_t)pk->nb_wires * 32, cudaMemcpyDeviceToDevice, st));
+      B200ZK_CUDA(ctx, cudaMemcpyAsync(pk->blinding, peer_ptr(pk, 0, pk->blinding), 9 * 32, cudaMemcpyDeviceToDevice, st));
+    }
+  }
   std::vector<Fe4> pub(pk->nb_public);  // public inputs, bound into the transcript
   if (pk->nb_public) {
     if (solution_host) memcpy(pub.data(), solution_host, (size_t)pk->nb_public * 32);
@@ -941,11 +1178,24 @@ static int prove_impl(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solution
   B200ZK_TRY(to_canonical(ctx, pk->qk, log2n));
 
   // P9: Lagrange-coset forms on the big domain
-  B200ZK_TRY(to_coset(ctx, pk->bl, n + 2, pk->el, logb));
-  B200ZK_TRY(to_coset(ctx, pk->br, n + 2, pk->er, logb));
-  B200ZK_TRY(to_coset(ctx, pk->bo, n + 2, pk->eo, logb));
-  B200ZK_TRY(to_coset(ctx, pk->bz, n + 3, pk->ez, logb));
-  B200ZK_TRY(to_coset(ctx, pk->qk, n, pk->eqk, logb));
+  if (dist) {
+    B200ZK_TRY(to_coset_dist(ctx, pk, pk->bl, n + 2, pk->el, 0));
+    B200ZK_TRY(to_coset_dist(ctx, pk, pk->br, n + 2, pk->er, 1));
+    B200ZK_TRY(to_coset_dist(ctx, pk, pk->bo, n + 2, pk->eo, 2));
+    B200ZK_TRY(to_coset_dist(ctx, pk, pk->bz, n + 3, pk->ez, 3));
+    B200ZK_TRY(to_coset_dist(ctx, pk, pk->qk, n, pk->eqk, 4));
+    // z(wX) at a position of this rank's range sits in the neighbour's range when there are more ranks than points of
+    // the big domain per point of the small one; the neighbour finished ez before it entered the barrier of the
+    // transform after it
+    if (pk->log2g > log_ratio)
+      B200ZK_CUDA(ctx, cudaMemcpyAsync(db.ez_other, peer_ptr(pk, pk->rank ^ 1u, pk->ez), db.local * 32, cudaMemcpyDeviceToDevice, st));
+  } else {
+    B200ZK_TRY(to_coset(ctx, pk->bl, n + 2, pk->el, logb));
+    B200ZK_TRY(to_coset(ctx, pk->br, n + 2, pk->er, logb));
+    B200ZK_TRY(to_coset(ctx, pk->bo, n + 2, pk->eo, logb));
+    B200ZK_TRY(to_coset(ctx, pk->bz, n + 3, pk->ez, logb));
+    B200ZK_TRY(to_coset(ctx, pk->qk, n, pk->eqk, logb));
+  }
 
   B200ZK_TRY(commit_join(ctx));
   B200ZK_TRY(fetch_points(ctx, pk, 11, 1, pts + 64 * 3));  // pts[3] = Z
@@ -963,6 +1213,19 @@ static int prove_impl(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solution
     q.out = pk->t;
     q.log_big = logb;
     q.log_ratio = log_ratio;
+    q.base = 0;
+    q.count = N4;
+    q.log_local = logb;
+    q.ez_other = pk->ez;
+    if (dist) {
+      // this rank's contiguous range of the bit-reversed coset evaluations; the key's forms are read at the same range
+      q.base = db.local * pk->rank;
+      q.count = db.local;
+      q.log_local = logb - pk->log2g;
+      q.ez_other = db.ez_other;
+      q.ql += 2 * q.base; q.qr += 2 * q.base; q.qm += 2 * q.base; q.qo += 2 * q.base;
+      q.s1 += 2 * q.base; q.s2 += 2 * q.base; q.s3 += 2 * q.base; q.lone += 2 * q.base;
+    }
     q.alpha = to_arg(alpha); q.beta = to_arg(beta); q.gamma = to_arg(gamma);
     const Fe4 u = host::from_u64(HFR, 5);
     const Fe4 bu = host::mul(HFR, beta, u);
@@ -989,10 +1252,28 @@ static int prove_impl(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solution
         }
       }
     }
-    k_quotient<<<nblocks(N4, 256), 256, 0, st>>>(q);
+    k_quotient<<<nblocks(q.count, 256), 256, 0, st>>>(q);
     B200ZK_LAUNCH_CHECK(ctx, "k_quotient");
   }
-  B200ZK_TRY(ntt_run(ctx, pk->t, logb, 1, B200ZK_DIT, 1));  // h, canonical, natural order
+  if (dist) {
+    // four-step DIT: strides < C on the range this rank holds (exchange fused into its last pass), strides >= C on the
+    // column-block shard X[r][c_lo] in the exchange buffer; then every rank collects all column blocks (peer DMA, 2-D
+    // copies) into the natural-order h — only the rows that hold the 3(n+2) coefficients
+    void* peers[8] = {};
+    for (unsigned k = 0; k < pk->world; k++) peers[k] = peer_ptr(pk, k, db.xb[1]);
+    B200ZK_TRY(ntt_dist_run(ctx, pk->t, pk->t, logb, pk->log2g, pk->rank, pk->dist_log2c, 0, 1, B200ZK_DIT, 1, peers));
+    B200ZK_TRY(group_barrier(ctx, pk));
+    B200ZK_TRY(ntt_dist_run(ctx, db.xb[1], db.xb[1], logb, pk->log2g, pk->rank, pk->dist_log2c, 1, 1, B200ZK_DIT, 1));
+    B200ZK_TRY(group_barrier(ctx, pk));
+    const size_t C = (size_t)1 << pk->dist_log2c, C_loc = C >> pk->log2g;
+    size_t rows = (3 * (n + 2) + C - 1) / C;
+    if (rows > (N4 >> pk->dist_log2c)) rows = N4 >> pk->dist_log2c;
+    for (unsigned k = 0; k < pk->world; k++)
+      B200ZK_CUDA(ctx, cudaMemcpy2DAsync(pk->t + 2 * (k * C_loc), C * 32, peer_ptr(pk, k, db.xb[1]), C_loc * 32, C_loc * 32, rows,
+                                         cudaMemcpyDeviceToDevice, st));
+  } else {
+    B200ZK_TRY(ntt_run(ctx, pk->t, logb, 1, B200ZK_DIT, 1));  // h, canonical, natural order
+  }
 
   // P12: commit h1, h2, h3
   const size_t m = n + 2;
@@ -1113,7 +1394,13 @@ static int prove_impl(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solution
   }
   B200ZK_TRY(divide_x_minus_a(ctx, pk, pk->folded, n + 3, zeta, pk->quot));
   B200ZK_TRY(commit(ctx, pk, pk->quot, n + 2, 2));  // slot 2: BatchedProof.H
+  uint32_t dist_err = 0;
+  if (dist) B200ZK_CUDA(ctx, cudaMemcpyAsync(&dist_err, pk->dist_err, 4, cudaMemcpyDeviceToHost, st));
   B200ZK_TRY(fetch_points(ctx, pk, 2, 1, pts + 64 * 7));
+  if (dist_err) {
+    snprintf(ctx->cuda_err, sizeof(ctx->cuda_err), "multi-GPU prover: a rank did not reach a barrier within 20 s");
+    return B200ZK_ERR_CUDA;
+  }
 
   // proof blob: LRO[3], Z, H[3], BatchedProof.H, ZShiftedOpening.H (64 B each) | claimed[7], Z(w*zeta) (32 B each)
   uint8_t* outp = (uint8_t*)proof_out;
@@ -1127,7 +1414,9 @@ extern "C" {
 
 int b200zk_plonk_prove(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solution_host, const void* blinding_host,
                        void* proof_out) {
-  if (!ctx || !pk || !solution_host || !blinding_host || !proof_out) return B200ZK_ERR_BAD_ARG;
+  if (!ctx || !pk || !proof_out) return B200ZK_ERR_BAD_ARG;
+  const bool follower = pk->world > 1 && pk->rank != 0;  // takes solution and blinding from rank 0 over NVLink
+  if (!follower && (!solution_host || !blinding_host)) return B200ZK_ERR_BAD_ARG;
   B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
   return prove_impl(ctx, pk, solution_host, blinding_host, proof_out);
 }

@@ -275,13 +275,87 @@ class ProvingKey:
         _lib.check(self.ctx.handle, self.ctx.lib.b200zk_plonk_pk_poly(self.ctx.handle, self.handle, which, out.ctypes.data))
         return out.tobytes()
 
+    # ---- multi-GPU: one key per GPU, the ranks prove together (b200zk_plonk_join) -------------------------
+    def arena(self):
+        """(device pointer, bytes) of the key's arena — what the other ranks map"""
+        base, nbytes = C.c_void_p(), C.c_size_t()
+        _lib.check(self.ctx.handle, self.ctx.lib.b200zk_plonk_arena(self.ctx.handle, self.handle, C.byref(base), C.byref(nbytes)))
+        return base.value, nbytes.value
+
+    def Join(self, group=None) -> None:
+        """Join the ranks of a torch.distributed group (one process per GPU of one box) into one prover: every rank
+        holds a key set up for the same circuit; the arenas are mapped into each other through CUDA IPC handles
+        exchanged once (all_gather), after which no collective is on the data path.  Afterwards every rank calls
+        Prove (ranks > 0 may pass None for solution and blinding) and gets the same proof."""
+        import torch
+        import torch.distributed as dist
+
+        lib, h = self.ctx.lib, self.ctx.handle
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        base, _ = self.arena()
+        handle = (C.c_ubyte * 64)()
+        _lib.check(h, lib.b200zk_ipc_export(h, C.c_void_p(base), handle))
+        dev = "cuda:%d" % self.ctx.device
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+        allh = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine, group=group)
+        ptrs = (C.c_void_p * world)()
+        self._imported = []
+        for k in range(world):
+            if k == rank:
+                ptrs[k] = base
+            else:
+                raw = (C.c_ubyte * 64)(*allh[k].cpu().tolist())
+                out = C.c_void_p()
+                _lib.check(h, lib.b200zk_ipc_import(h, raw, C.byref(out)))
+                ptrs[k] = out.value
+                self._imported.append(out)
+        _lib.check(h, lib.b200zk_plonk_join(h, self.handle, rank, world, ptrs))
+        self._group = group
+        self.rank, self.world = rank, world
+
+    @staticmethod
+    def JoinLocal(keys: Sequence["ProvingKey"]) -> None:
+        """The same for keys that live in ONE process (one context per key, on one or several GPUs): the arena pointers
+        are valid as they are.  Every key must then be proved from its own host thread (the ranks wait for each other
+        on the device).  Keys that share one DEVICE (tests) need CUDA_MODULE_LOADING=EAGER and one hardware queue per
+        stream (CUDA_DEVICE_MAX_CONNECTIONS=32): a waiting rank must never be behind a context-wide synchronisation."""
+        world = len(keys)
+        ptrs = (C.c_void_p * world)(*[k.arena()[0] for k in keys])
+        for r, k in enumerate(keys):
+            _lib.check(k.ctx.handle, k.ctx.lib.b200zk_plonk_join(k.ctx.handle, k.handle, r, world, ptrs))
+            k.rank, k.world, k._imported, k._group = r, world, [], None
+
+    def Leave(self) -> None:
+        """back to single-GPU proving (collective over the group when the key was joined with Join)"""
+        if getattr(self, "world", 1) <= 1:
+            return
+        lib, h = self.ctx.lib, self.ctx.handle
+        _lib.check(h, lib.b200zk_plonk_leave(h, self.handle))
+        if self._imported:
+            import torch.distributed as dist
+
+            dist.barrier(group=self._group)   # nobody unmaps an arena a peer may still be reading
+            for p in self._imported:
+                lib.b200zk_ipc_close(h, p)
+            dist.barrier(group=self._group)
+        self._imported = []
+        self.world, self.rank = 1, 0
+
     def Prove(self, solution, blinding) -> Proof:
         """plonk.Prove: solution = every wire's value (public wires first), blinding = 9 fr.SetRandom draws
-        (Montgomery images, order L,L,R,R,O,O,Z,Z,Z)."""
+        (Montgomery images, order L,L,R,R,O,O,Z,Z,Z).  Joined keys: ranks > 0 may pass None for both."""
+        out = np.zeros(832, dtype=np.uint8)
+        if solution is None:
+            assert getattr(self, "world", 1) > 1 and self.rank != 0, "only ranks > 0 of a joined key take the solution from rank 0"
+            rc = self.ctx.lib.b200zk_plonk_prove(self.ctx.handle, self.handle, None, None, out.ctypes.data)
+            if rc == _lib.ERR_UNSATISFIED:
+                raise UnsatisfiedConstraint(self.ctx.lib.b200zk_plonk_unsatisfied_row(self.handle) - self.nb_public)
+            _lib.check(self.ctx.handle, rc)
+            return Proof(out.tobytes())
         sol = np.ascontiguousarray(np.frombuffer(bytes(solution), dtype=np.uint8) if not isinstance(solution, np.ndarray) else solution)
         bl = np.ascontiguousarray(np.frombuffer(bytes(blinding), dtype=np.uint8) if not isinstance(blinding, np.ndarray) else blinding)
         assert sol.nbytes == self.nb_wires * 32 and bl.nbytes == 9 * 32
-        out = np.zeros(832, dtype=np.uint8)
         rc = self.ctx.lib.b200zk_plonk_prove(self.ctx.handle, self.handle, sol.ctypes.data, bl.ctypes.data, out.ctypes.data)
         if rc == _lib.ERR_UNSATISFIED:  # plonk.Prove returns spr.Solve's error before committing to anything
             row = self.ctx.lib.b200zk_plonk_unsatisfied_row(self.handle)
@@ -310,6 +384,8 @@ class ProvingKey:
 
     def close(self) -> None:
         if self.handle and self.ctx.handle:
+            if getattr(self, "world", 1) > 1 and not getattr(self, "_imported", None):
+                self.ctx.lib.b200zk_plonk_leave(self.ctx.handle, self.handle)
             self.ctx.lib.b200zk_plonk_pk_free(self.ctx.handle, self.handle)
         self.handle = None
 
