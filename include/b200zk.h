@@ -128,6 +128,12 @@ size_t b200zk_bases_len(const b200zk_bases* bases);
 
 int b200zk_msm_g1(b200zk_ctx* ctx, const b200zk_bases* bases, const void* scalars_host, size_t n,
                   void* out_affine_host /* 64 B */);
+/* One rank's share of a point-range-sharded MultiExp fed from the host: scalars_host[0..n) pair with
+ * bases[first_base .. first_base+n); the extended-Jacobian partial (128 B) is left at out_partial_dev for the
+ * cross-GPU combination (all-gather + b200zk_g1_sum_dev).  Same chunked copy / compute overlap as b200zk_msm_g1;
+ * asynchronous on the context stream once the copies are enqueued. */
+int b200zk_msm_g1_shard(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const void* scalars_host, size_t n,
+                        void* out_partial_dev);
 /* Device-resident variant.  first_base = index of the base paired with scalars[0] (point-range shard).
  * out_kind 0: canonical affine (64 B); 1: extended-Jacobian partial X,Y,ZZ,ZZZ (128 B) to be combined across
  * GPUs with b200zk_g1_sum_dev.  Asynchronous on the context stream. */
@@ -139,7 +145,7 @@ int b200zk_g1_sum_dev(b200zk_ctx* ctx, const void* partials_dev, size_t count, v
  * 2 = two-level scatter (partition by high bucket bits, then shared-memory cursors; slower on B200, kept for comparison) */
 int b200zk_msm_set_flat_scatter(b200zk_ctx* ctx, int on);
 /* b200zk_msm_g1 (host scalars) splits large inputs by point range so that the host-to-device copy of one chunk runs
- * under the MSM of the previous one; 0 = choose from n (2 chunks from 2^23 points: measured best, scripts/e2e_chunks.py), 1 = never split, up to 8 */
+ * under the MSM of the previous one; 0 = choose from n (from 2^23 points: three chunks of 1/8, 3/8 and 1/2 of the points — only the first copy is exposed), 1 = never split, up to 8 equal chunks */
 int b200zk_msm_set_host_chunks(b200zk_ctx* ctx, int chunks);
 /* tests / tuning: buckets per running-sum chunk of the bucket reduction, as a power of two: 3 (short dependent chains,
  * chosen up to 2^17 buckets where the reduction is latency-bound), 4 (up to 2^19 buckets), 5 (fewer chunk results, chosen

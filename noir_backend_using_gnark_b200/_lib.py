@@ -81,6 +81,7 @@ def load() -> C.CDLL:
         "b200zk_bases_free": (None, [vp, vp]),
         "b200zk_bases_len": (sz, [vp]),
         "b200zk_msm_g1": (i, [vp, vp, vp, sz, vp]),
+        "b200zk_msm_g1_shard": (i, [vp, vp, sz, vp, sz, vp]),
         "b200zk_msm_windows": (i, [vp, vp, sz]),
         "b200zk_msm_set_host_chunks": (i, [vp, i]),
         "b200zk_msm_set_small_path": (i, [vp, i]),

@@ -282,6 +282,22 @@ def MultiExp(srs: SRS, scalars, n: Optional[int] = None, first_base: int = 0, ou
     return res.tobytes()
 
 
+def MultiExpShard(srs: SRS, scalars_host, n: Optional[int] = None, first_base: int = 0, out=None):
+    """One rank's share of a point-range-sharded MultiExp, fed from HOST scalars (b200zk_msm_g1_shard): the chunked
+    PCIe copy runs under the bucket work; the 128-byte extended-Jacobian partial stays on the device (CUDA tensor) for
+    the cross-GPU all-gather + SumPartials."""
+    import torch
+
+    ctx = srs.ctx
+    ptr, keep = _host_ptr(scalars_host)
+    if n is None:
+        n = (keep.nbytes if hasattr(keep, "nbytes") else len(scalars_host)) // 32
+    if out is None:
+        out = torch.empty(128, dtype=torch.uint8, device="cuda:%d" % ctx.device)
+    _lib.check(ctx.handle, ctx.lib.b200zk_msm_g1_shard(ctx.handle, srs.handle, first_base, ptr, n, out.data_ptr()))
+    return out
+
+
 def Commit(p, srs: SRS):
     """kzg.Commit(p, srs): MultiExp of the polynomial's coefficients against srs.G1[:len(p)]."""
     return MultiExp(srs, p)

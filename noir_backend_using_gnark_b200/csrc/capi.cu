@@ -307,46 +307,73 @@ int b200zk_msm_g1_dev(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_b
   return msm_run(ctx, bases, first_base, scalars_dev, n, out_dev, out_kind);
 }
 
-int b200zk_msm_g1(b200zk_ctx* ctx, const b200zk_bases* bases, const void* scalars_host, size_t n,
-                  void* out_affine_host) {
-  B200ZK_TRY(enter(ctx));
-  if (!bases || !out_affine_host || (n && !scalars_host) || n > bases->n) return B200ZK_ERR_BAD_ARG;
-  const size_t head = 64 + 8 * 128;  // result + up to 8 partial sums
+// host scalars -> result left on the device (stage + 0: affine, or extended-Jacobian partial), on the context stream
+static int msm_host_scalars(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const void* scalars_host, size_t n,
+                            int out_kind, char** result_dev) {
+  const size_t head = 128 + 8 * 128;  // result + up to 8 partial sums
   const size_t bytes = n * 32 + head;
   B200ZK_TRY(ensure(ctx, ctx->stage, bytes));
   char* stage = (char*)ctx->stage.p;
   char* sc = stage + head;
-  // Large inputs are split by point range so that the PCIe copy of chunk i+1 runs under the MSM of chunk i
-  // (the sum of the partial MSMs is the MSM: the canonical affine result does not depend on the split).
-  unsigned chunks = ctx->msm_host_chunks > 0 ? (unsigned)ctx->msm_host_chunks : (n >= ((size_t)1 << 23) ? 2u : 1u);
+  *result_dev = stage;
+  // Large inputs are split by point range so that the PCIe copy of chunk i+1 runs under the MSM of chunk i (the sum of
+  // the partial MSMs is the MSM: the canonical affine result does not depend on the split).  Only the copy of the FIRST
+  // chunk is exposed, so the automatic split is uneven — 1/8, 3/8, 1/2 of the points: a short first copy, and every
+  // later copy still shorter than the MSM it hides under.
+  unsigned chunks = ctx->msm_host_chunks > 0 ? (unsigned)ctx->msm_host_chunks : (n >= ((size_t)1 << 23) ? 3u : 1u);
   if (chunks > 8) chunks = 8;
   if (n < 4096 * (size_t)chunks) chunks = 1;
   if (chunks == 1) {
     if (n) B200ZK_CUDA(ctx, cudaMemcpyAsync(sc, scalars_host, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-    B200ZK_TRY(msm_run(ctx, bases, 0, sc, n, stage, 0));
+    return msm_run(ctx, bases, first_base, sc, n, stage, out_kind);
+  }
+  size_t bound[9];
+  if (ctx->msm_host_chunks == 0) {
+    bound[0] = 0; bound[1] = n / 8; bound[2] = n / 2; bound[3] = n;
   } else {
     const size_t per = (n + chunks - 1) / chunks;
-    // the copy stream must not overtake earlier work on the compute stream that still reads the staging buffer
-    B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
-    B200ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
-    auto copy_chunk = [&](unsigned i) -> int {
-      const size_t first = (size_t)i * per, cnt = first + per <= n ? per : n - first;
+    for (unsigned i = 0; i <= chunks; i++) bound[i] = (size_t)i * per < n ? (size_t)i * per : n;
+  }
+  // the copy stream must not overtake earlier work on the compute stream that still reads the staging buffer
+  B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+  B200ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+  auto copy_chunk = [&](unsigned i) -> int {
+    const size_t first = bound[i], cnt = bound[i + 1] - first;
+    if (cnt)
       B200ZK_CUDA(ctx, cudaMemcpyAsync(sc + first * 32, (const char*)scalars_host + first * 32, cnt * 32, cudaMemcpyHostToDevice,
                                        ctx->side));
-      B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev_chunk[i], ctx->side));
-      return B200ZK_OK;
-    };
-    B200ZK_TRY(copy_chunk(0));
-    for (unsigned i = 0; i < chunks; i++) {
-      if (i + 1 < chunks) B200ZK_TRY(copy_chunk(i + 1));
-      const size_t first = (size_t)i * per, cnt = first + per <= n ? per : n - first;
-      B200ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[i], 0));
-      B200ZK_TRY(msm_run(ctx, bases, first, sc + first * 32, cnt, stage + 64 + 128 * i, 1));
-    }
-    B200ZK_TRY(g1_sum_run(ctx, stage + 64, chunks, stage));
+    B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev_chunk[i], ctx->side));
+    return B200ZK_OK;
+  };
+  B200ZK_TRY(copy_chunk(0));
+  for (unsigned i = 0; i < chunks; i++) {
+    if (i + 1 < chunks) B200ZK_TRY(copy_chunk(i + 1));
+    const size_t first = bound[i], cnt = bound[i + 1] - first;
+    B200ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[i], 0));
+    B200ZK_TRY(msm_run(ctx, bases, first_base + first, sc + first * 32, cnt, stage + 128 + 128 * i, 1));
   }
-  B200ZK_CUDA(ctx, cudaMemcpyAsync(out_affine_host, stage, 64, cudaMemcpyDeviceToHost, ctx->stream));
+  return g1_sum_run(ctx, stage + 128, chunks, stage, out_kind);
+}
+
+int b200zk_msm_g1(b200zk_ctx* ctx, const b200zk_bases* bases, const void* scalars_host, size_t n,
+                  void* out_affine_host) {
+  B200ZK_TRY(enter(ctx));
+  if (!bases || !out_affine_host || (n && !scalars_host) || n > bases->n) return B200ZK_ERR_BAD_ARG;
+  char* result = nullptr;
+  B200ZK_TRY(msm_host_scalars(ctx, bases, 0, scalars_host, n, 0, &result));
+  B200ZK_CUDA(ctx, cudaMemcpyAsync(out_affine_host, result, 64, cudaMemcpyDeviceToHost, ctx->stream));
   B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200ZK_OK;
+}
+
+int b200zk_msm_g1_shard(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const void* scalars_host, size_t n,
+                        void* out_partial_dev) {
+  B200ZK_TRY(enter(ctx));
+  if (!bases || !out_partial_dev || (n && !scalars_host) || first_base > bases->n || n > bases->n - first_base)
+    return B200ZK_ERR_BAD_ARG;
+  char* result = nullptr;
+  B200ZK_TRY(msm_host_scalars(ctx, bases, first_base, scalars_host, n, 1, &result));
+  B200ZK_CUDA(ctx, cudaMemcpyAsync(out_partial_dev, result, 128, cudaMemcpyDeviceToDevice, ctx->stream));
   return B200ZK_OK;
 }
 
@@ -376,7 +403,7 @@ int b200zk_msm_set_host_chunks(b200zk_ctx* ctx, int chunks) {
 
 int b200zk_g1_sum_dev(b200zk_ctx* ctx, const void* partials_dev, size_t count, void* out_affine_dev) {
   B200ZK_TRY(enter(ctx));
-  return g1_sum_run(ctx, partials_dev, count, out_affine_dev);
+  return g1_sum_run(ctx, partials_dev, count, out_affine_dev, 0);
 }
 
 int b200zk_srs_generate(b200zk_ctx* ctx, const void* alpha_host, size_t first, size_t n, b200zk_bases** out) {

@@ -179,7 +179,8 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
             void* out_dev, int out_kind, int lane = 0);
 int msm_precompute_run(b200zk_ctx* ctx, b200zk_bases* bases, int c);
 unsigned msm_window_count(const b200zk_ctx* ctx, const b200zk_bases* bases, size_t n);
-int g1_sum_run(b200zk_ctx* ctx, const void* partials_dev, size_t count, void* out_affine_dev);
+// out_kind 0: canonical affine (64 B); 1: extended-Jacobian sum (128 B)
+int g1_sum_run(b200zk_ctx* ctx, const void* partials_dev, size_t count, void* out_dev, int out_kind = 0);
 int srs_decompress_run(b200zk_ctx* ctx, const void* compressed_host, size_t n, void* out_dev, unsigned* bad_count);
 int srs_compress_run(b200zk_ctx* ctx, const void* points_dev, size_t n, void* out_host);
 int microbench_run(b200zk_ctx* ctx, int which, double* out_ops_per_s);

@@ -546,15 +546,15 @@ __global__ void msm_final_kernel(const void* __restrict__ set_sums, MsmShape sh,
   }
 }
 
-__global__ void g1_sum_kernel(const void* __restrict__ partials, unsigned count, void* __restrict__ out) {
+__global__ void g1_sum_kernel(const void* __restrict__ partials, unsigned count, void* __restrict__ out, int out_kind) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   G1XYZZ total = g1_xyzz_inf();
   for (unsigned i = 0; i < count; i++) {
     G1XYZZ q = g1_load_xyzz(partials, i);
     g1_add(total, q);
   }
-  G1Affine r = g1_to_affine_single(total);
-  g1_store_affine(out, 0, r);
+  if (out_kind == 0) g1_store_affine(out, 0, g1_to_affine_single(total));
+  else g1_store_xyzz(out, 0, total);
 }
 
 __global__ void iota_u32_kernel(unsigned* __restrict__ dst, size_t n) {
@@ -950,9 +950,9 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
   return B200ZK_OK;
 }
 
-int g1_sum_run(b200zk_ctx* ctx, const void* partials_dev, size_t count, void* out_affine_dev) {
-  if (!partials_dev || !out_affine_dev) return B200ZK_ERR_BAD_ARG;
-  g1_sum_kernel<<<1, 32, 0, ctx->stream>>>(partials_dev, (unsigned)count, out_affine_dev);
+int g1_sum_run(b200zk_ctx* ctx, const void* partials_dev, size_t count, void* out_dev, int out_kind) {
+  if (!partials_dev || !out_dev) return B200ZK_ERR_BAD_ARG;
+  g1_sum_kernel<<<1, 32, 0, ctx->stream>>>(partials_dev, (unsigned)count, out_dev, out_kind);
   B200ZK_LAUNCH_CHECK(ctx, "g1_sum_kernel");
   return B200ZK_OK;
 }
