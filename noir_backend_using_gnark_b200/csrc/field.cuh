@@ -251,9 +251,9 @@ __device__ __forceinline__ Fe<P> fe_dbl(const Fe<P>& a) {
   return fe_add(a, a);
 }
 
-// Montgomery product a*b/R mod modulus, fully reduced.
+// Montgomery product a*b/R mod modulus, fully reduced: schoolbook CIOS (136 IMAD.WIDE + 8 IMAD).
 template <class P>
-__device__ __forceinline__ Fe<P> fe_mul(const Fe<P>& a, const Fe<P>& b) {
+__device__ __forceinline__ Fe<P> fe_mul_schoolbook(const Fe<P>& a, const Fe<P>& b) {
   uint32_t E[8], O[8], top, c;
   // step 0
   mulw4(E, a.l[0], a.l[2], a.l[4], a.l[6], b.l[0]);
@@ -302,6 +302,201 @@ __device__ __forceinline__ Fe<P> fe_mul(const Fe<P>& a, const Fe<P>& b) {
         "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]));
   final_sub<P>(r.l);
   return r;
+}
+
+// Montgomery reduction of a 16-limb value T < modulus * 2^256: R <- (R + q*m) / 2^32 + T[8+i] * 2^224, eight times (the
+// same even/odd IMAD.WIDE chains as fe_mul with the upper limbs injected one per step); result fully reduced.
+template <class P>
+__device__ __forceinline__ Fe<P> mont_reduce16(const uint32_t* T) {
+  uint32_t Ee[8], Oo[8], top, c = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    Ee[k] = T[k];
+    Oo[k] = 0;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    top = 0;
+    uint32_t q = (Ee[0] + c) * P::NINV;
+    madw4_top(Ee, top, P::M0, P::M2, P::M4, P::M6, q);
+    madw4_cin(Oo, Ee[0], c, P::M1, P::M3, P::M5, P::M7, q);
+    c = Ee[1];
+    uint32_t s_lo, s_hi;
+    asm("add.cc.u32 %0, %2, %3;\n\t"
+        "addc.u32 %1, 0, 0;"
+        : "=r"(s_lo), "=r"(s_hi)
+        : "r"(top), "r"(T[8 + i]));
+    uint32_t nO[8] = {Ee[2], Ee[3], Ee[4], Ee[5], Ee[6], Ee[7], s_lo, s_hi};
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      Ee[k] = Oo[k];
+      Oo[k] = nO[k];
+    }
+  }
+  Fe<P> r;
+  asm("add.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32 %7, %15, %23;"
+      : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]),
+        "=r"(r.l[7])
+      : "r"(Ee[0]), "r"(Ee[1]), "r"(Ee[2]), "r"(Ee[3]), "r"(Ee[4]), "r"(Ee[5]), "r"(Ee[6]), "r"(Ee[7]), "r"(c),
+        "r"(Oo[0]), "r"(Oo[1]), "r"(Oo[2]), "r"(Oo[3]), "r"(Oo[4]), "r"(Oo[5]), "r"(Oo[6]));
+  final_sub<P>(r.l);
+  return r;
+}
+
+// ---- 4 x 4 limb product (128 x 128 -> 256 bits), 16 IMAD.WIDE: products x_k*y_j with k+j even fill 64-bit slots aligned at
+// even limbs (E), those with k+j odd fill slots aligned at odd limbs (O); r = E + (O << 32)
+__device__ __forceinline__ void kchain2_2(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1) {
+  asm("mad.lo.cc.u32 %0, %6, %8, %0;\n\t"
+      "madc.hi.cc.u32 %1, %6, %8, %1;\n\t"
+      "madc.lo.cc.u32 %2, %7, %9, %2;\n\t"
+      "madc.hi.cc.u32 %3, %7, %9, %3;\n\t"
+      "addc.cc.u32 %4, %4, 0;\n\t"
+      "addc.u32 %5, %5, 0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5])
+      : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void kchain3_1(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t b0, uint32_t b1,
+                                          uint32_t b2) {
+  asm("mad.lo.cc.u32 %0, %7, %10, %0;\n\t"
+      "madc.hi.cc.u32 %1, %7, %10, %1;\n\t"
+      "madc.lo.cc.u32 %2, %8, %11, %2;\n\t"
+      "madc.hi.cc.u32 %3, %8, %11, %3;\n\t"
+      "madc.lo.cc.u32 %4, %9, %12, %4;\n\t"
+      "madc.hi.cc.u32 %5, %9, %12, %5;\n\t"
+      "addc.u32 %6, %6, 0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(b0), "r"(b1), "r"(b2));
+}
+__device__ __forceinline__ void kchain1_3(uint32_t* acc, uint32_t a0, uint32_t b0) {
+  asm("mad.lo.cc.u32 %0, %5, %6, %0;\n\t"
+      "madc.hi.cc.u32 %1, %5, %6, %1;\n\t"
+      "addc.cc.u32 %2, %2, 0;\n\t"
+      "addc.cc.u32 %3, %3, 0;\n\t"
+      "addc.u32 %4, %4, 0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4])
+      : "r"(a0), "r"(b0));
+}
+
+__device__ __forceinline__ void mul4x4(uint32_t* r, const uint32_t* x, const uint32_t* y) {
+  auto put = [](uint32_t* dst, uint32_t u, uint32_t v) {
+    uint64_t p = (uint64_t)u * v;
+    dst[0] = (uint32_t)p;
+    dst[1] = (uint32_t)(p >> 32);
+  };
+  uint32_t E[8], O[7];
+  put(E + 0, x[0], y[0]); put(E + 2, x[0], y[2]); put(E + 4, x[1], y[3]); put(E + 6, x[3], y[3]);
+  kchain2_2(E + 2, x[1], x[2], y[1], y[2]);
+  kchain2_2(E + 2, x[2], x[3], y[0], y[1]);
+  put(O + 0, x[0], y[1]); put(O + 2, x[0], y[3]); put(O + 4, x[2], y[3]);
+  O[6] = 0;
+  kchain3_1(O, x[1], x[1], x[3], y[0], y[2], y[2]);
+  kchain1_3(O + 2, x[2], y[1]);
+  kchain1_3(O + 2, x[3], y[0]);
+  r[0] = E[0];
+  asm("add.cc.u32 %0, %7, %14;\n\t"
+      "addc.cc.u32 %1, %8, %15;\n\t"
+      "addc.cc.u32 %2, %9, %16;\n\t"
+      "addc.cc.u32 %3, %10, %17;\n\t"
+      "addc.cc.u32 %4, %11, %18;\n\t"
+      "addc.cc.u32 %5, %12, %19;\n\t"
+      "addc.u32 %6, %13, %20;"
+      : "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(O[0]), "r"(O[1]), "r"(O[2]), "r"(O[3]),
+        "r"(O[4]), "r"(O[5]), "r"(O[6]));
+}
+
+// r[0..4] = a[0..3] + b[0..3] (r[4] = carry)
+__device__ __forceinline__ void add4c(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  asm("add.cc.u32 %0, %5, %9;\n\t"
+      "addc.cc.u32 %1, %6, %10;\n\t"
+      "addc.cc.u32 %2, %7, %11;\n\t"
+      "addc.cc.u32 %3, %8, %12;\n\t"
+      "addc.u32 %4, 0, 0;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]));
+}
+
+// Montgomery product with one level of Karatsuba on the 8 x 8 limb product: 3 x 16 IMAD.WIDE for a*b (instead of 64),
+// then the reduction sweep (64 + 8).  Same result as fe_mul_schoolbook (fully reduced; the whole GPU suite passes with it
+// as the production multiplier).  Measured alternative, not the default: see fe_mul below.
+template <class P>
+__device__ __forceinline__ Fe<P> fe_mul_k(const Fe<P>& a, const Fe<P>& b) {
+  uint32_t z0[8], z2[8], m[9], sa[5], sb[5];
+  mul4x4(z0, a.l, b.l);
+  mul4x4(z2, a.l + 4, b.l + 4);
+  add4c(sa, a.l, a.l + 4);
+  add4c(sb, b.l, b.l + 4);
+  mul4x4(m, sa, sb);
+  // m += (ca ? sb_lo : 0) << 128 + (cb ? sa_lo : 0) << 128 + (ca & cb) << 256
+  {
+    const uint32_t ma = 0u - sa[4], mb = 0u - sb[4];
+    uint32_t u[4], v[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      u[i] = sb[i] & ma;
+      v[i] = sa[i] & mb;
+    }
+    m[8] = sa[4] & sb[4];
+    asm("add.cc.u32 %0, %0, %5;\n\t"
+        "addc.cc.u32 %1, %1, %6;\n\t"
+        "addc.cc.u32 %2, %2, %7;\n\t"
+        "addc.cc.u32 %3, %3, %8;\n\t"
+        "addc.u32 %4, %4, 0;"
+        : "+r"(m[4]), "+r"(m[5]), "+r"(m[6]), "+r"(m[7]), "+r"(m[8])
+        : "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]));
+    asm("add.cc.u32 %0, %0, %5;\n\t"
+        "addc.cc.u32 %1, %1, %6;\n\t"
+        "addc.cc.u32 %2, %2, %7;\n\t"
+        "addc.cc.u32 %3, %3, %8;\n\t"
+        "addc.u32 %4, %4, 0;"
+        : "+r"(m[4]), "+r"(m[5]), "+r"(m[6]), "+r"(m[7]), "+r"(m[8])
+        : "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]));
+  }
+  // m -= z0 + z2   (the middle term a0*b1 + a1*b0 >= 0, < 2^257)
+#pragma unroll
+  for (int pass = 0; pass < 2; pass++) {
+    const uint32_t* z = pass ? z2 : z0;
+    asm("sub.cc.u32 %0, %0, %9;\n\t"
+        "subc.cc.u32 %1, %1, %10;\n\t"
+        "subc.cc.u32 %2, %2, %11;\n\t"
+        "subc.cc.u32 %3, %3, %12;\n\t"
+        "subc.cc.u32 %4, %4, %13;\n\t"
+        "subc.cc.u32 %5, %5, %14;\n\t"
+        "subc.cc.u32 %6, %6, %15;\n\t"
+        "subc.cc.u32 %7, %7, %16;\n\t"
+        "subc.u32 %8, %8, 0;"
+        : "+r"(m[0]), "+r"(m[1]), "+r"(m[2]), "+r"(m[3]), "+r"(m[4]), "+r"(m[5]), "+r"(m[6]), "+r"(m[7]), "+r"(m[8])
+        : "r"(z[0]), "r"(z[1]), "r"(z[2]), "r"(z[3]), "r"(z[4]), "r"(z[5]), "r"(z[6]), "r"(z[7]));
+  }
+  // T = z0 + (m << 128) + (z2 << 256)
+  uint32_t T[16];
+#pragma unroll
+  for (int i = 0; i < 4; i++) T[i] = z0[i];
+  asm("add.cc.u32 %0, %12, %20;\n\t"
+      "addc.cc.u32 %1, %13, %21;\n\t"
+      "addc.cc.u32 %2, %14, %22;\n\t"
+      "addc.cc.u32 %3, %15, %23;\n\t"
+      "addc.cc.u32 %4, %16, %24;\n\t"
+      "addc.cc.u32 %5, %17, %25;\n\t"
+      "addc.cc.u32 %6, %18, %26;\n\t"
+      "addc.cc.u32 %7, %19, %27;\n\t"
+      "addc.cc.u32 %8, %29, %28;\n\t"
+      "addc.cc.u32 %9, %30, 0;\n\t"
+      "addc.cc.u32 %10, %31, 0;\n\t"
+      "addc.u32 %11, %32, 0;"
+      : "=r"(T[4]), "=r"(T[5]), "=r"(T[6]), "=r"(T[7]), "=r"(T[8]), "=r"(T[9]), "=r"(T[10]), "=r"(T[11]), "=r"(T[12]),
+        "=r"(T[13]), "=r"(T[14]), "=r"(T[15])
+      : "r"(z0[4]), "r"(z0[5]), "r"(z0[6]), "r"(z0[7]), "r"(z2[0]), "r"(z2[1]), "r"(z2[2]), "r"(z2[3]),
+        "r"(m[0]), "r"(m[1]), "r"(m[2]), "r"(m[3]), "r"(m[4]), "r"(m[5]), "r"(m[6]), "r"(m[7]), "r"(m[8]),
+        "r"(z2[4]), "r"(z2[5]), "r"(z2[6]), "r"(z2[7]));
+  return mont_reduce16<P>(T);
 }
 
 // acc += sum_k a_k*b_k * 2^(64k), carry rippling through 2 more limbs (caller guarantees no carry out)
@@ -457,47 +652,20 @@ __device__ __forceinline__ Fe<P> fe_sqr(const Fe<P>& x) {
         "+r"(T[9]), "+r"(T[10]), "+r"(T[11]), "+r"(T[12]), "+r"(T[13]), "+r"(T[14]), "+r"(T[15])
       : "r"(D[0]), "r"(D[1]), "r"(D[2]), "r"(D[3]), "r"(D[4]), "r"(D[5]), "r"(D[6]), "r"(D[7]), "r"(D[8]), "r"(D[9]),
         "r"(D[10]), "r"(D[11]), "r"(D[12]), "r"(D[13]), "r"(D[14]), "r"(D[15]));
-  // Montgomery reduction of T: R <- (R + q*m) / 2^32 + T[8+i] * 2^224, eight times
-  uint32_t Ee[8], Oo[8], top, c = 0;
-#pragma unroll
-  for (int k = 0; k < 8; k++) {
-    Ee[k] = T[k];
-    Oo[k] = 0;
-  }
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    top = 0;
-    uint32_t q = (Ee[0] + c) * P::NINV;
-    madw4_top(Ee, top, P::M0, P::M2, P::M4, P::M6, q);
-    madw4_cin(Oo, Ee[0], c, P::M1, P::M3, P::M5, P::M7, q);
-    c = Ee[1];
-    uint32_t s_lo, s_hi;
-    asm("add.cc.u32 %0, %2, %3;\n\t"
-        "addc.u32 %1, 0, 0;"
-        : "=r"(s_lo), "=r"(s_hi)
-        : "r"(top), "r"(T[8 + i]));
-    uint32_t nO[8] = {Ee[2], Ee[3], Ee[4], Ee[5], Ee[6], Ee[7], s_lo, s_hi};
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      Ee[k] = Oo[k];
-      Oo[k] = nO[k];
-    }
-  }
-  Fe<P> r;
-  asm("add.cc.u32 %0, %8, %16;\n\t"
-      "addc.cc.u32 %1, %9, %17;\n\t"
-      "addc.cc.u32 %2, %10, %18;\n\t"
-      "addc.cc.u32 %3, %11, %19;\n\t"
-      "addc.cc.u32 %4, %12, %20;\n\t"
-      "addc.cc.u32 %5, %13, %21;\n\t"
-      "addc.cc.u32 %6, %14, %22;\n\t"
-      "addc.u32 %7, %15, %23;"
-      : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]),
-        "=r"(r.l[7])
-      : "r"(Ee[0]), "r"(Ee[1]), "r"(Ee[2]), "r"(Ee[3]), "r"(Ee[4]), "r"(Ee[5]), "r"(Ee[6]), "r"(Ee[7]), "r"(c),
-        "r"(Oo[0]), "r"(Oo[1]), "r"(Oo[2]), "r"(Oo[3]), "r"(Oo[4]), "r"(Oo[5]), "r"(Oo[6]));
-  final_sub<P>(r.l);
-  return r;
+  return mont_reduce16<P>(T);
+}
+
+// The product every kernel uses: the schoolbook CIOS form.  The Karatsuba form (-DB200ZK_KARATSUBA_MUL) has 112 instead
+// of 127 IMAD.WIDE per product but measured SLOWER on B200 (63.5 vs 67.3 G/s; MSM 2^24 48.4 vs 40.3 ms; NTT 2^24 4.14 vs
+// 3.52 ms): ptxas places 22 of its extra moves / carry adds on the multiplier pipe as IMAD.MOV / IMAD.IADD / IMAD.X and
+// the hot kernels start to spill — profiles/r02_fieldmul.md.
+template <class P>
+__device__ __forceinline__ Fe<P> fe_mul(const Fe<P>& a, const Fe<P>& b) {
+#ifdef B200ZK_KARATSUBA_MUL
+  return fe_mul_k(a, b);
+#else
+  return fe_mul_schoolbook(a, b);
+#endif
 }
 
 // Montgomery form -> regular integer (multiply by 1)

@@ -5,6 +5,7 @@
 //   which = 2: fr Montgomery multiplications per second
 //   which = 3: FP64 DFMA per second (8 independent chains per thread) -- the other multiplier array of the SM
 //   which = 4: IMAD.WIDE.U32 per second while the same threads also issue DFMA (1:1), to see whether the pipes overlap
+//   which = 5 / 6: fp multiplications per second in the schoolbook CIOS form / with the Karatsuba product (field.cuh)
 #include "common.cuh"
 #include "field.cuh"
 
@@ -87,6 +88,26 @@ __global__ void __launch_bounds__(256) mb_mixed_kernel(unsigned long long* out, 
   if (s == 0x12345678u && fs == 0.12345) out[0] = s;
 }
 
+template <class P, int FORM>
+__global__ void __launch_bounds__(256) mb_mul_form_kernel(uint4* out, unsigned seed) {
+  // FORM 0: schoolbook CIOS, 1: Karatsuba product + reduction sweep; also checks the two against each other once
+  Fe<P> x = fe_one<P>(), y = fe_one<P>(), m = fe_one<P>();
+  x.l[0] ^= seed + threadIdx.x;
+  y.l[1] ^= seed + blockIdx.x + 7u * threadIdx.x;
+  m.l[2] ^= seed + 3u * threadIdx.x;
+  for (int it = 0; it < MB_ITERS; it++) {
+    if (FORM == 0) {
+      x = fe_mul_schoolbook(x, m);
+      y = fe_mul_schoolbook(y, m);
+    } else {
+      x = fe_mul_k(x, m);
+      y = fe_mul_k(y, m);
+    }
+  }
+  Fe<P> s = fe_add(x, y);
+  if (s.l[0] == 0x12345678u && s.l[7] == 0x9abcdef0u) fe_store(out, s);
+}
+
 template <class P>
 __global__ void __launch_bounds__(256) mb_mul_kernel(uint4* out, unsigned seed) {
   Fe<P> x = fe_one<P>(), y = fe_one<P>(), m = fe_one<P>();
@@ -104,7 +125,7 @@ __global__ void __launch_bounds__(256) mb_mul_kernel(uint4* out, unsigned seed) 
 }
 
 int microbench_run(b200zk_ctx* ctx, int which, double* out_ops_per_s) {
-  if (!out_ops_per_s || which < 0 || which > 4) return B200ZK_ERR_BAD_ARG;
+  if (!out_ops_per_s || which < 0 || which > 6) return B200ZK_ERR_BAD_ARG;
   void* sink = nullptr;
   B200ZK_CUDA(ctx, cudaMalloc(&sink, 64));
   cudaEvent_t e0, e1;
@@ -117,6 +138,8 @@ int microbench_run(b200zk_ctx* ctx, int which, double* out_ops_per_s) {
     if (which == 0) mb_imad_kernel<<<blocks, threads, 0, ctx->stream>>>((unsigned long long*)sink, 17u + rep);
     else if (which == 1) mb_mul_kernel<FpParams><<<blocks, threads, 0, ctx->stream>>>((uint4*)sink, 17u + rep);
     else if (which == 2) mb_mul_kernel<FrParams><<<blocks, threads, 0, ctx->stream>>>((uint4*)sink, 17u + rep);
+    else if (which == 5) mb_mul_form_kernel<FpParams, 0><<<blocks, threads, 0, ctx->stream>>>((uint4*)sink, 17u + rep);
+    else if (which == 6) mb_mul_form_kernel<FpParams, 1><<<blocks, threads, 0, ctx->stream>>>((uint4*)sink, 17u + rep);
     else if (which == 3) mb_dfma_kernel<<<blocks, threads, 0, ctx->stream>>>((double*)sink, 17u + rep);
     else mb_mixed_kernel<<<blocks, threads, 0, ctx->stream>>>((unsigned long long*)sink, 17u + rep);
     B200ZK_LAUNCH_CHECK(ctx, "microbench kernel");
