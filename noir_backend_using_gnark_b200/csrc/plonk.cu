@@ -5,7 +5,9 @@
 //   gather L,R,O | blind | copy-constraint ratio (batch inversion + prefix product) | quotient on the 4n coset
 //   (gate + permutation + L1 terms, division by X^n-1 fused) | Horner evaluations | division by (X - a) |
 //   linearised polynomial | folds.  The Fiat-Shamir transcript (SHA-256) and the O(1) challenge scalars are host code.
+#include <cstdlib>
 #include <new>
+#include <utility>
 #include <vector>
 #include "common.cuh"
 #include "consts.cuh"
@@ -491,7 +493,7 @@ struct PeerSet {
 // Stream-ordered barrier: thread t publishes `epoch` in slot [rank] of peer t's flag array, then waits until slot [t]
 // of the own array has reached it.  Epochs only grow, so a peer that is already one barrier ahead also satisfies the
 // wait.  A peer that never arrives (crashed process) raises *err after 20 s instead of hanging the device.
-__global__ void k_group_barrier(PeerSet ps, size_t flags_off, size_t err_off, unsigned epoch) {
+__global__ void k_group_barrier(PeerSet ps, size_t flags_off, size_t err_off, unsigned epoch) {  // flags_off: of the channel
   const unsigned t = threadIdx.x;
   if (t >= ps.world) return;
   __threadfence_system();
@@ -582,7 +584,7 @@ struct b200zk_plonk_pk {
   uint32_t* flags = nullptr;     // [world] arrival epochs written by the peers
   uint32_t* dist_err = nullptr;  // raised by a barrier that timed out
   void* gather = nullptr;        // 16 x 128 B: this rank's extended-Jacobian partial per commitment slot
-  unsigned epoch = 0;
+  unsigned epoch[2] = {0, 0};    // barrier channel 0: context stream; 1: MSM lane 1 (forked commitments)
 };
 
 namespace {
@@ -657,11 +659,13 @@ T* peer_ptr(const b200zk_plonk_pk* pk, unsigned k, T* local) {
   return reinterpret_cast<T*>(pk->peer_base[k] + (reinterpret_cast<const char*>(local) - pk->arena));
 }
 
-// stream-ordered barrier over the ranks; all ranks issue their barriers in the same (program) order
-int group_barrier(b200zk_ctx* ctx, b200zk_plonk_pk* pk) {
-  pk->epoch++;
-  k_group_barrier<<<1, 32, 0, ctx->stream>>>(peer_set(pk), (size_t)((char*)pk->flags - pk->arena),
-                                             (size_t)((char*)pk->dist_err - pk->arena), pk->epoch);
+// stream-ordered barrier over the ranks; all ranks issue the barriers of one channel in the same (program) order.
+// Channel 0 lives on the context stream, channel 1 on MSM lane 1 (a forked commitment runs beside the context stream).
+int group_barrier(b200zk_ctx* ctx, b200zk_plonk_pk* pk, int channel = 0) {
+  pk->epoch[channel]++;
+  cudaStream_t st = channel ? ctx->ws[1].stream : ctx->stream;
+  k_group_barrier<<<1, 32, 0, st>>>(peer_set(pk), (size_t)((char*)pk->flags - pk->arena) + 32 * (size_t)channel,
+                                    (size_t)((char*)pk->dist_err - pk->arena), pk->epoch[channel]);
   B200ZK_LAUNCH_CHECK(ctx, "k_group_barrier");
   return B200ZK_OK;
 }
@@ -764,10 +768,23 @@ int commit_many(b200zk_ctx* ctx, const b200zk_plonk_pk* pk, const uint4* const* 
 // one commitment on MSM lane 1 while the context stream continues with work that neither needs its result nor
 // rewrites its input; commit_join() orders the context stream after it
 int commit_fork(b200zk_ctx* ctx, const b200zk_plonk_pk* pk, const uint4* poly, size_t len, int slot) {
-  if (pk->commit_hook || ctx->msm_single_lane || is_dist(pk)) return commit(ctx, pk, poly, len, slot);
+  if (pk->commit_hook || ctx->msm_single_lane) return commit(ctx, pk, poly, len, slot);
   B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
   B200ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->ws[1].stream, ctx->ev_fork, 0));
-  B200ZK_TRY(msm_run(ctx, pk->bases, 0, poly, len, (char*)pk->points + 64 * slot, 0, 1));
+  if (is_dist(pk)) {
+    // this rank's share on lane 1, the lane's own barrier channel, then the sum of all ranks' partials — all beside the
+    // context stream
+    b200zk_plonk_pk* mpk = const_cast<b200zk_plonk_pk*>(pk);
+    const size_t lo = len * pk->rank / pk->world, hi = len * (pk->rank + 1) / pk->world;
+    B200ZK_TRY(msm_run(ctx, pk->bases, lo, poly + 2 * lo, hi - lo, (char*)pk->gather + 128 * slot, 1, 1));
+    B200ZK_TRY(group_barrier(ctx, mpk, 1));
+    SumSlots sl;
+    for (int k = 0; k < 8; k++) sl.slot[k] = slot;
+    k_sum_partials_peers<<<1, 32, 0, ctx->ws[1].stream>>>(peer_set(pk), (size_t)((char*)pk->gather - pk->arena), sl, pk->points);
+    B200ZK_LAUNCH_CHECK(ctx, "k_sum_partials_peers");
+  } else {
+    B200ZK_TRY(msm_run(ctx, pk->bases, 0, poly, len, (char*)pk->points + 64 * slot, 0, 1));
+  }
   B200ZK_CUDA(ctx, cudaEventRecord(ctx->ws[1].done, ctx->ws[1].stream));
   ctx->lane_pending = true;
   return B200ZK_OK;
@@ -821,6 +838,35 @@ int divide_x_minus_a(b200zk_ctx* ctx, const b200zk_plonk_pk* pk, const uint4* f,
   B200ZK_LAUNCH_CHECK(ctx, "k_div_apply");
   return B200ZK_OK;
 }
+
+// B200ZK_PROVE_TRACE=1: device time between the prover's stages (CUDA events on the context stream), printed to stderr
+struct ProveTrace {
+  bool on;
+  cudaStream_t st;
+  std::vector<std::pair<const char*, cudaEvent_t>> ev;
+  explicit ProveTrace(cudaStream_t s) : on(getenv("B200ZK_PROVE_TRACE") != nullptr), st(s) { mark("start"); }
+  void mark(const char* label) {
+    if (!on) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, st);
+    ev.emplace_back(label, e);
+  }
+  ~ProveTrace() {
+    if (!on || ev.empty()) return;
+    cudaEventSynchronize(ev.back().second);
+    float total = 0;
+    cudaEventElapsedTime(&total, ev.front().second, ev.back().second);
+    fprintf(stderr, "[b200zk prove trace] total %.3f ms:", total);
+    for (size_t i = 1; i < ev.size(); i++) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev[i - 1].second, ev[i].second);
+      fprintf(stderr, " %s %.3f", ev[i].first, ms);
+    }
+    fprintf(stderr, "\n");
+    for (auto& e : ev) cudaEventDestroy(e.second);
+  }
+};
 
 struct Transcript {
   // fiatshamir.Transcript with sha256: challenge_i = H(name_i || challenge_{i-1} || bindings_i)
@@ -1106,6 +1152,7 @@ static int prove_impl(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solution
     else B200ZK_CUDA(ctx, cudaMemcpyAsync(pub.data(), pk->sol, (size_t)pk->nb_public * 32, cudaMemcpyDeviceToHost, st));
   }
 
+  ProveTrace tr(st);
   // P1-P4: L,R,O in Lagrange form, canonical, blinded, committed
   k_gather_lro<<<nblocks(n, 256), 256, 0, st>>>(pk->sol, pk->lro, n, pk->l, pk->r, pk->o);
   B200ZK_LAUNCH_CHECK(ctx, "k_gather_lro");
@@ -1119,17 +1166,28 @@ static int prove_impl(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solution
   uint4* lag[3] = {pk->l, pk->r, pk->o};
   uint4* can[3] = {pk->bl, pk->br, pk->bo};
   for (int k = 0; k < 3; k++) {
+    if (dist && (unsigned)k % pk->world != pk->rank) continue;  // multi-GPU: rank k mod g makes polynomial k, the others fetch it
     B200ZK_CUDA(ctx, cudaMemcpyAsync(can[k], lag[k], n * 32, cudaMemcpyDeviceToDevice, st));
     B200ZK_CUDA(ctx, cudaMemsetAsync((char*)can[k] + n * 32, 0, 8 * 32, st));
     B200ZK_TRY(to_canonical(ctx, can[k], log2n));
     k_blind<<<1, 32, 0, st>>>(can[k], n, pk->blinding + 2 * (2 * k), 2);
     B200ZK_LAUNCH_CHECK(ctx, "k_blind");
   }
+  if (dist) {
+    B200ZK_TRY(group_barrier(ctx, pk));
+    for (int k = 0; k < 3; k++) {
+      const unsigned owner = (unsigned)k % pk->world;
+      if (owner != pk->rank)
+        B200ZK_CUDA(ctx, cudaMemcpyAsync(can[k], peer_ptr(pk, owner, can[k]), (n + 8) * 32, cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  tr.mark("lro_canonical");
   {
     const size_t clen[3] = {n + 2, n + 2, n + 2};
     const int cslot[3] = {8, 9, 10};
     B200ZK_TRY(commit_many(ctx, pk, can, clen, cslot, 3));
   }
+  tr.mark("lro_commit");
   B200ZK_TRY(fetch_points(ctx, pk, 8, 3, pts));  // pts[0..2] = LRO (the sync also lands bad_row)
   pk->last_bad_row = bad_row == 0xffffffffu ? -1 : (long long)bad_row;
   if (pk->last_bad_row >= 0) return B200ZK_ERR_UNSATISFIED;
@@ -1167,6 +1225,7 @@ static int prove_impl(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solution
   B200ZK_LAUNCH_CHECK(ctx, "k_blind");
   // the commitment to Z runs on an MSM lane of its own while the context stream prepares what the quotient needs and
   // that does not depend on alpha (P8, P9)
+  tr.mark("z_build");
   B200ZK_TRY(commit_fork(ctx, pk, pk->bz, n + 3, 11));
 
   // P8: qk completed with the public inputs, canonical
@@ -1176,6 +1235,7 @@ static int prove_impl(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solution
     B200ZK_LAUNCH_CHECK(ctx, "k_set_public");
   }
   B200ZK_TRY(to_canonical(ctx, pk->qk, log2n));
+  tr.mark("qk");
 
   // P9: Lagrange-coset forms on the big domain
   if (dist) {
@@ -1197,7 +1257,9 @@ static int prove_impl(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solution
     B200ZK_TRY(to_coset(ctx, pk->qk, n, pk->eqk, logb));
   }
 
+  tr.mark("coset_ntts");
   B200ZK_TRY(commit_join(ctx));
+  tr.mark("z_commit_join");
   B200ZK_TRY(fetch_points(ctx, pk, 11, 1, pts + 64 * 3));  // pts[3] = Z
   fs.begin("alpha");
   fs.bind_point(pts + 64 * 3);
@@ -1255,6 +1317,7 @@ static int prove_impl(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solution
     k_quotient<<<nblocks(q.count, 256), 256, 0, st>>>(q);
     B200ZK_LAUNCH_CHECK(ctx, "k_quotient");
   }
+  tr.mark("quotient");
   if (dist) {
     // four-step DIT: strides < C on the range this rank holds (exchange fused into its last pass), strides >= C on the
     // column-block shard X[r][c_lo] in the exchange buffer; then every rank collects all column blocks (peer DMA, 2-D
@@ -1275,6 +1338,7 @@ static int prove_impl(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solution
     B200ZK_TRY(ntt_run(ctx, pk->t, logb, 1, B200ZK_DIT, 1));  // h, canonical, natural order
   }
 
+  tr.mark("h_intt");
   // P12: commit h1, h2, h3
   const size_t m = n + 2;
   {
@@ -1283,6 +1347,7 @@ static int prove_impl(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solution
     const int cslot[3] = {12, 13, 14};
     B200ZK_TRY(commit_many(ctx, pk, hp, clen, cslot, 3));
   }
+  tr.mark("h_commit");
   B200ZK_TRY(fetch_points(ctx, pk, 12, 3, pts + 64 * 4));  // pts[4..6] = H
   fs.begin("zeta");
   for (int i = 0; i < 3; i++) fs.bind_point(pts + 64 * (4 + i));
@@ -1302,6 +1367,7 @@ static int prove_impl(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solution
   B200ZK_TRY(eval_poly(ctx, pk, pk->s1, n, zeta, 3));
   B200ZK_TRY(eval_poly(ctx, pk, pk->s2, n, zeta, 4));
   B200ZK_TRY(eval_poly(ctx, pk, pk->bz, n + 3, zeta_shift, 5));
+  tr.mark("evals");
   B200ZK_TRY(fetch_scalars(ctx, pk, 0, 6, sc));
   const Fe4 lz = sc[0], rz = sc[1], oz = sc[2], s1z = sc[3], s2z = sc[4], zu = sc[5];
 
@@ -1363,7 +1429,9 @@ static int prove_impl(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solution
     hf::g1_to_image(hf::g1j_to_affine(hf::g1j_add_affine(hf::g1_msm_small(hp, hs), hf::g1_from_image(pts + 64 * 4))),
                     pts + 64 * 10);
   }
+  tr.mark("zs_div_lin_fold_evals");
   B200ZK_TRY(commit_join(ctx));  // the lane of ZShiftedOpening.H (pk->quot is rewritten below)
+  tr.mark("zs_commit_join");
   B200ZK_TRY(fetch_scalars(ctx, pk, 6, 2, sc + 6));
   B200ZK_TRY(fetch_points(ctx, pk, 15, 1, pts + 64 * 8));  // pts[8] = ZShiftedOpening.H
   const Fe4 claimed[7] = {sc[6], sc[7], lz, rz, oz, s1z, s2z};
@@ -1393,7 +1461,9 @@ static int prove_impl(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solution
     B200ZK_LAUNCH_CHECK(ctx, "k_fold7");
   }
   B200ZK_TRY(divide_x_minus_a(ctx, pk, pk->folded, n + 3, zeta, pk->quot));
+  tr.mark("fold_div");
   B200ZK_TRY(commit(ctx, pk, pk->quot, n + 2, 2));  // slot 2: BatchedProof.H
+  tr.mark("batched_commit");
   uint32_t dist_err = 0;
   if (dist) B200ZK_CUDA(ctx, cudaMemcpyAsync(&dist_err, pk->dist_err, 4, cudaMemcpyDeviceToHost, st));
   B200ZK_TRY(fetch_points(ctx, pk, 2, 1, pts + 64 * 7));
