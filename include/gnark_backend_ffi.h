@@ -15,8 +15,10 @@
  *   - SRS            : $XDG_CONFIG_HOME|$HOME/.config + /noir-lang/srs.hex, hex of kzg.SRS.WriteTo, generated with a
  *                      fresh random alpha when unreadable (backend/common.go:78-144).  Size: 1_000_000 points as in
  *                      common.go:137 unless B200ZK_SRS_SIZE is set (needed for circuits above 2^19 rows).
- * Test hook (not in the reference): B200ZK_BLINDING_SEED=<u64> makes the 9 blinding draws of the prover deterministic
- * (SplitMix64 stream standing in for crypto/rand.Reader) so proofs can be compared byte for byte.
+ * Test hook (not in the reference, not part of this header's export list): the library also exports
+ * b200zk_ffi_test_seed_blinding(uint64 seed, int enable), which makes the 9 blinding draws of the prover deterministic
+ * (SplitMix64 stream standing in for crypto/rand.Reader) so proofs can be compared byte for byte.  Nothing in the
+ * environment can enable it.
  */
 #ifndef GNARK_BACKEND_FFI_H
 #define GNARK_BACKEND_FFI_H

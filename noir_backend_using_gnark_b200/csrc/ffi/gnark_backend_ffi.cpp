@@ -16,6 +16,7 @@
 #include <list>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "../../../include/b200zk.h"
@@ -501,14 +502,21 @@ struct HexOut {
   }
 };
 
-size_t pk_stream_bytes(const Keyed& k) {  // ProvingKey.WriteTo size
-  return k.vk_bytes.size() + 2 * (8 + 5 * 32) + 9 * (4 + 32 * k.n) + 4 + 8 * 3 * k.n;
+// ProvingKey.WriteTo size.  The nine polynomials are []fr.Element (u32 count + elements); pk.Permutation is a []int64
+// that gnark-crypto's encoder hands to binary.Write as it is: 3n big-endian int64 with NO count (ReadFrom sizes it from
+// Domain[0].Cardinality).
+size_t pk_stream_bytes(const Keyed& k) {
+  return k.vk_bytes.size() + 2 * (8 + 5 * 32) + 9 * (4 + 32 * k.n) + 8 * 3 * k.n;
 }
 
 // the 9 blinding scalars of plonk.Prove: fr.SetRandom draws (their limbs are the Montgomery form)
+// Tests pin the draws through the explicit entry point b200zk_ffi_test_seed_blinding (below); nothing in the
+// environment can switch the shipping library to predictable blinding.
+bool g_seeded_blinding = false;
+uint64_t g_blinding_seed = 0;
 void draw_blinding(Fe4 blinding[9]) {
-  if (const char* seed = getenv("B200ZK_BLINDING_SEED")) {
-    uint64_t st = strtoull(seed, nullptr, 0);
+  if (g_seeded_blinding) {
+    uint64_t st = g_blinding_seed;
     for (int i = 0; i < 9;) {
       Fe4 v;
       for (int j = 0; j < 4; j++) {
@@ -544,9 +552,23 @@ bool felts_count(Span h, size_t* count) {
 }  // namespace
 
 // ================================================================================================ exports
+// The Go exports are reentrant; this library keeps per-process state (SRS, circuits, device keys), so the exports
+// serialise on one lock.
+std::mutex g_export_lock;
+
 extern "C" {
 
+// TEST-ONLY entry point (not in the reference, not declared in include/gnark_backend_ffi.h's export list): pins the 9
+// blinding draws of the following proofs to a splitmix64 stream so that proof bytes can be compared with the CPU checker's.
+// enable = 0 returns to /dev/urandom.  Proofs made with a known seed are NOT zero-knowledge.
+void b200zk_ffi_test_seed_blinding(uint64_t seed, int enable) {
+  std::lock_guard<std::mutex> hold(g_export_lock);
+  g_seeded_blinding = enable != 0;
+  g_blinding_seed = seed;
+}
+
 struct PlonkPreprocess_return PlonkPreprocess(GoString acirJSON, GoString encodedRandomValues) {  // main.go:58-78
+  std::lock_guard<std::mutex> hold(g_export_lock);
   Trace trace("PlonkPreprocess");
   // the Rust side sends a JSON-quoted hex string (plonk/mod.rs:197-203); main.go:66-72 un-quotes it
   Span quoted = span_of(encodedRandomValues);
@@ -607,9 +629,6 @@ struct PlonkPreprocess_return PlonkPreprocess(GoString acirJSON, GoString encode
     }
     for (size_t i = 0; i < 3 * n; i++)
       if (perm[i] == -1) perm[i] = cycle[lro[i]];
-    std::vector<uint8_t> len;
-    put_u32(len, (uint32_t)(3 * n));
-    out.put(len);
     char* dst = out.reserve(8 * 3 * n);
     parallel_for(3 * n, 1 << 16, [&](size_t b, size_t e) {
       for (size_t i = b; i < e; i++) {
@@ -627,6 +646,7 @@ struct PlonkPreprocess_return PlonkPreprocess(GoString acirJSON, GoString encode
 }
 
 char* PlonkProveWithPK(GoString acirJSON, GoString encodedValues, GoString encodedProvingKey) {  // main.go:24-37
+  std::lock_guard<std::mutex> hold(g_export_lock);
   Trace trace("PlonkProveWithPK");
   const Span payload = span_of(encodedValues);
   size_t nvalues = 0;
@@ -654,7 +674,9 @@ char* PlonkProveWithPK(GoString acirJSON, GoString encodedValues, GoString encod
   {
     Span pk = span_of(encodedProvingKey);
     if (pk.n % 2) fatal("encoding/hex: odd length hex string");
-    if (pk.n != 2 * pk_stream_bytes(k)) fatal(pk.n < 2 * pk_stream_bytes(k) ? "unexpected EOF reading the proving key" : "proving key does not belong to this circuit (size mismatch)");
+    // (keys written by round-1 builds of this library carried a 4-byte count before Permutation: still accepted)
+    if (pk.n != 2 * pk_stream_bytes(k) && pk.n != 2 * (pk_stream_bytes(k) + 4))
+      fatal(pk.n < 2 * pk_stream_bytes(k) ? "unexpected EOF reading the proving key" : "proving key does not belong to this circuit (size mismatch)");
     std::vector<uint8_t> head = hex_decode(Span{pk.p, 2 * k.vk_bytes.size()});
     if (head != k.vk_bytes) fatal("proving key does not belong to this circuit and SRS");
   }
@@ -695,6 +717,7 @@ uint8_t PlonkVerifyWithMeta(GoString, GoString, GoString) { return 0; }  // main
 
 uint8_t PlonkVerifyWithVK(GoString acirJSON, GoString encodedProof, GoString encodedPublicInputs,
                           GoString encodedVerifyingKey) {  // main.go:44-56, plonk.go:29-51
+  std::lock_guard<std::mutex> hold(g_export_lock);
   Trace trace("PlonkVerifyWithVK");
   ParsedProof proof = parse_proof(hex_decode(span_of(encodedProof)));
   ParsedVk vk = parse_vk(hex_decode(span_of(encodedVerifyingKey)));
@@ -718,6 +741,9 @@ uint8_t PlonkVerifyWithVK(GoString acirJSON, GoString encodedProof, GoString enc
     pub[i] = lazy ? felt_from_hex(Span{payload.p + 8 + 64 * src, 64}) : values[src];
   }
   trace("circuit read / found");
+  // plonk.Verify refuses a public witness whose length differs from vk.NbPublicVariables ("invalid witness size"):
+  // the reference then returns false (plonk.go:47-49)
+  if (vk.nb_public != pub.size()) return 0;
   ensure_srs();  // vk.InitKZG(srs): the G2 elements live in the SRS file
   const bool ok = plonk_verify(proof, vk, pub, state().g2, state().g2_prepared);
   trace("plonk.Verify (host pairing)");

@@ -59,8 +59,17 @@ def load_ffi() -> C.CDLL:
     lib.PlonkVerifyWithVK.argtypes = [GoString, GoString, GoString, GoString]
     lib.PlonkPreprocess.restype = KeyPair
     lib.PlonkPreprocess.argtypes = [GoString, GoString]
+    lib.b200zk_ffi_test_seed_blinding.restype = None
+    lib.b200zk_ffi_test_seed_blinding.argtypes = [C.c_uint64, C.c_int]
     _ffi = lib
     return lib
+
+
+def seed_blinding(seed=None) -> None:
+    """TEST-ONLY: pin the prover's 9 blinding draws to a SplitMix64 stream (seed) so that proof bytes can be compared with
+    the CPU checker's; None returns to /dev/urandom.  Seeded proofs are not zero-knowledge."""
+    lib = load_ffi()
+    lib.b200zk_ffi_test_seed_blinding(0 if seed is None else int(seed) & 0xFFFFFFFFFFFFFFFF, 0 if seed is None else 1)
 
 
 def encode_felts(values: Sequence[int]) -> str:

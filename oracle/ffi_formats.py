@@ -66,9 +66,11 @@ def _vector_bytes(v: Sequence[int]) -> bytes:
 
 
 def pk_bytes(pk: pl.ProvingKey) -> bytes:
-    """plonk ProvingKey.WriteTo: Vk | Domain[0] | Domain[1] | Ql Qr Qm Qo CQk LQk S1 S2 S3 | Permutation (u32 len, i64s)."""
+    """plonk ProvingKey.WriteTo: Vk | Domain[0] | Domain[1] | Ql Qr Qm Qo CQk LQk S1 S2 S3 | Permutation.
+    The polynomials are []fr.Element (u32 count + elements); Permutation is a []int64 that gnark-crypto's Encoder passes
+    to binary.Write unchanged: 3n big-endian int64, no count (ReadFrom sizes it from Domain[0].Cardinality)."""
     out = vk_bytes(pk.vk) + _domain_bytes(pk.n) + _domain_bytes(pk.n_big)
     for poly in (pk.ql, pk.qr, pk.qm, pk.qo, pk.cqk, pk.lqk, pk.s1, pk.s2, pk.s3):
         out += _vector_bytes(poly)
-    out += len(pk.permutation).to_bytes(4, "big") + b"".join(int(x).to_bytes(8, "big") for x in pk.permutation)
+    out += b"".join(int(x).to_bytes(8, "big") for x in pk.permutation)
     return out

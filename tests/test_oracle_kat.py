@@ -6,6 +6,7 @@ it does pin is r-1 used as the coefficient -1 at /root/reference/gnark_backend_f
 import json
 import os
 
+import numpy as np
 import pytest
 
 from oracle import bn254 as o
@@ -153,3 +154,29 @@ def test_pseudo_random_bases_are_on_the_curve_and_in_the_group():
     for x, y in pts:
         assert (y * y - x * x * x - 3) % o.P_MOD == 0
     assert o.g1_mul(pts[0], o.R_MOD) is None            # cofactor 1: every curve point has order r
+
+
+# ---- external anchors: alt_bn128 precompile vectors (EIP-196) as shipped in go-ethereum's core/vm/testdata/precompiles
+# (bn256Add.json / bn256ScalarMul.json, cases "chfast1"): points that were NOT produced by this repository
+EIP196_ADD = ("18b18acfb4c2c30276db5411368e7185b311dd124691610c5d3b74034e093dc9", "063c909c4720840cb5134cb9f59fa749755796819658d32efc0d288198f37266",
+              "07c2b7f58a84bd6145f00c9c2bc0bb1a187f20ff2c92963a88019e7c6a014eed", "06614e20c147e940f2d70da3f74c9a17df361706a4485c742bd6788478fa17d7",
+              "2243525c5efd4b9c3d3c45ac0ca3fe4dd85e830a4ce6b65fa1eeaee202839703", "301d1d33be6da8e509df21cc35964723180eed7532537db9ae5e7d48f195c915")
+EIP196_MUL = ("2bd3e6d0f3b142924f5ca7b49ce5b9d54c4703d7ae5648e61d02268b1a0a9fb7", "21611ce0a6af85915e2f1d70300909ce2e49dfad4a4619c8390cae66cefdb204",
+              "00000000000000000000000000000000000000000000000011138ce750fa15c2",
+              "070a8d6a982153cae4be29d434e8faef8a47b274a053f5a4ee2a6c9c13c31e5c", "031b8ce914eba3a9ffb989f9cdd5b0f01943074bf4f0f315690ec3cec6981afc")
+
+
+def test_eip196_precompile_vectors_python_and_c_oracle():
+    ax, ay, bx, by, cx, cy = (int(v, 16) for v in EIP196_ADD)
+    assert o.g1_add((ax, ay), (bx, by)) == (cx, cy)
+    px, py, k, qx, qy = (int(v, 16) for v in EIP196_MUL)
+    assert o.g1_mul((px, py), k) == (qx, qy)
+    # the C restatement: affine addition, and the scalar multiplication as a one-term / two-term MultiExp
+    lib = cref.load()
+    A = np.frombuffer(o.g1_to_bytes([(ax, ay)]), dtype=np.uint8).copy()
+    B = np.frombuffer(o.g1_to_bytes([(bx, by)]), dtype=np.uint8).copy()
+    out = np.zeros(64, dtype=np.uint8)
+    lib.oracle_g1_add_affine(A.ctypes.data, B.ctypes.data, out.ctypes.data)
+    assert out.tobytes() == o.g1_to_bytes([(cx, cy)])
+    assert cref.msm(o.g1_to_bytes([(px, py)]), o.fr_to_mont_bytes([k]), 1, 1) == o.g1_to_bytes([(qx, qy)])
+    assert cref.msm(o.g1_to_bytes([(ax, ay), (bx, by)]), o.fr_to_mont_bytes([1, 1]), 2, 1) == o.g1_to_bytes([(cx, cy)])
