@@ -141,9 +141,6 @@ int b200zk_msm_g1_dev(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_b
                       size_t n, void* out_dev, int out_kind);
 /* out_affine_dev (64 B) = canonical affine of the sum of `count` extended-Jacobian partials (128 B each). */
 int b200zk_g1_sum_dev(b200zk_ctx* ctx, const void* partials_dev, size_t count, void* out_affine_dev);
-/* tests / tuning: 0 / 1 = one-level scatter (default: all of a point's returning atomics in flight at once),
- * 2 = two-level scatter (partition by high bucket bits, then shared-memory cursors; slower on B200, kept for comparison) */
-int b200zk_msm_set_flat_scatter(b200zk_ctx* ctx, int on);
 /* b200zk_msm_g1 (host scalars) splits large inputs by point range so that the host-to-device copy of one chunk runs
  * under the MSM of the previous one; 0 = choose from n (from 2^23 points: three chunks of 1/8, 3/8 and 1/2 of the points — only the first copy is exposed), 1 = never split, up to 8 equal chunks */
 int b200zk_msm_set_host_chunks(b200zk_ctx* ctx, int chunks);
@@ -185,7 +182,8 @@ int b200zk_msm_windows(const b200zk_ctx* ctx, const b200zk_bases* bases, size_t 
 typedef struct b200zk_plonk_pk b200zk_plonk_pk;
 /* Commitment hook: when set, every kzg.Commit inside b200zk_plonk_prove calls fn(user, scalars_dev, n, out_dev)
  * instead of the local MSM.  fn must leave the canonical affine commitment (64 B) at out_dev, ordered on the context
- * stream (b200zk_stream).  Used to shard the prover's MSMs over the GPUs of one box (dist_prove.py). */
+ * stream (b200zk_stream).  For hosts that bring their own commitment engine; the built-in multi-GPU prover does not
+ * use it (b200zk_plonk_join below) and refuses keys that have one. */
 typedef int (*b200zk_commit_fn)(void* user, const void* scalars_dev, size_t n, void* out_affine_dev);
 int b200zk_plonk_set_commit_hook(b200zk_plonk_pk* pk, b200zk_commit_fn fn, void* user);
 int b200zk_plonk_setup(b200zk_ctx* ctx, const b200zk_bases* bases, unsigned log2n, unsigned log2n_big,

@@ -89,7 +89,6 @@ def load() -> C.CDLL:
         "b200zk_msm_g1_dev": (i, [vp, vp, sz, vp, sz, vp, i]),
         "b200zk_g1_sum_dev": (i, [vp, vp, sz, vp]),
         "b200zk_msm_set_window": (i, [vp, i]),
-        "b200zk_msm_set_flat_scatter": (i, [vp, i]),
         "b200zk_plonk_setup": (i, [vp, vp, u, u, u, u, vp, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]),
         "b200zk_plonk_setup_r1cs": (i, [vp, vp, u, u, sz, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]),
         "b200zk_plonk_pk_free": (None, [vp, vp]),

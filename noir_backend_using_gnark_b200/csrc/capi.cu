@@ -86,7 +86,7 @@ void b200zk_destroy(b200zk_ctx* ctx) {
   for (int l = 0; l < MSM_LANES; l++) {
     MsmWorkspace& w = ctx->ws[l];
     DeviceBuf* bufs[] = {&w.msm_digits, &w.msm_sorted, &w.msm_counts, &w.msm_starts, &w.msm_cursor, &w.msm_buckets,
-                         &w.msm_tmp, &w.msm_small, &w.msm_scan_tmp, &w.msm_big, &w.msm_part};
+                         &w.msm_tmp, &w.msm_small, &w.msm_scan_tmp, &w.msm_big};
     for (auto bp : bufs) free_buf(*bp);
     if (l > 0 && w.stream) cudaStreamDestroy(w.stream);
     if (w.done) cudaEventDestroy(w.done);
@@ -516,11 +516,6 @@ int b200zk_ntt_set_radix2(b200zk_ctx* ctx, int on) {
   return B200ZK_OK;
 }
 
-int b200zk_msm_set_flat_scatter(b200zk_ctx* ctx, int on) {
-  if (!ctx) return B200ZK_ERR_BAD_ARG;
-  ctx->msm_flat_scatter = on;  // 0/1: one-level scatter (default), 2: two-level (partition + shared-memory cursors)
-  return B200ZK_OK;
-}
 
 int b200zk_msm_windows(const b200zk_ctx* ctx, const b200zk_bases* bases, size_t n) {
   if (!ctx || !bases || n == 0 || n > bases->n) return B200ZK_ERR_BAD_ARG;

@@ -47,7 +47,7 @@ namespace b200zk {
 static constexpr int MSM_LANES = 3;
 struct MsmWorkspace {
   DeviceBuf msm_digits, msm_sorted, msm_counts, msm_starts, msm_cursor, msm_buckets, msm_tmp, msm_small, msm_scan_tmp,
-      msm_big, msm_part;
+      msm_big;
   cudaStream_t stream = nullptr;   // lane 0: the context stream
   cudaEvent_t done = nullptr;      // recorded after the lane's last MSM (lanes > 0)
 };
@@ -83,7 +83,6 @@ struct b200zk_ctx {
   uint64_t launches = 0;
   char cuda_err[256] = {0};
   int forced_window = 0;
-  int msm_flat_scatter = 0;  // tests: force the one-level (global-atomic) scatter
   int ntt_radix2 = 0;  // tests: force the radix-2 pass kernel
   bool profiling = false;
   std::vector<b200zk::PhaseRecord> records;

@@ -10,7 +10,9 @@
 // Pipeline (all on the context stream, no host synchronisation):
 //   1 msm_hist_kernel        scalar: Montgomery -> regular, signed digits, bucket histogram (global atomics)
 //   2 exclusive scan          bucket start offsets (CUB)
-//   3 msm_scatter_kernel     counting sort: (table index | sign) grouped by bucket
+//   3 msm_scatter_kernel     counting sort: (table index | sign) grouped by bucket (two alternatives were built and
+//                            measured no better — a two-level partition + shared-memory scatter, and a CUB radix sort of
+//                            (bucket, entry) records: profiles/r02_msm_frontend.md)
 //   4 msm_accumulate_kernel  one thread per bucket walks its run: 64-byte affine gathers (next point prefetched),
 //                            extended-Jacobian mixed additions; over-long runs (skewed scalars) are left to
 //   4b msm_big_* kernels     which split a run over many CTAs and tree-reduce the partial sums in shared memory
@@ -169,79 +171,6 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint4* __restric
 #pragma unroll
   for (int w = 0; w < MAXW; w++)
     if (pos[w] != 0xffffffffu) sorted[pos[w]] = entry[w];
-}
-
-// ---- 3'. two-level scatter: partition by the high bits of the bucket id, then counting-sort each partition in
-// shared memory.  The one-level scatter above needs one RETURNING global atomic per entry (~31 G/s on B200, 6x slower
-// than non-returning reductions) and writes 4 bytes at random over hundreds of MB (8.7x DRAM write amplification, ncu).
-// Here the only returning global atomics are one per (CTA tile, partition); entries travel in ~1.5 KB runs to their
-// partition, and the final 4-byte stores of a partition land in a few MB that stay in L2.
-static constexpr int PART_TILE_PTS = 2048;    // points per CTA in the partition pass (8 per thread)
-static constexpr int MAX_PARTS = 1024;
-
-__global__ void __launch_bounds__(256) msm_partition_kernel(const uint4* __restrict__ scalars, size_t n, MsmShape sh,
-                                                            unsigned part_log, unsigned nparts,
-                                                            unsigned* __restrict__ part_cursor, uint2* __restrict__ tmp) {
-  __shared__ unsigned cnt[MAX_PARTS];
-  __shared__ unsigned base[MAX_PARTS];
-  for (unsigned p = threadIdx.x; p < nparts; p += blockDim.x) cnt[p] = 0;
-  __syncthreads();
-  const size_t tile0 = (size_t)blockIdx.x * PART_TILE_PTS;
-  // pass 1: count this tile's entries per partition
-  for (unsigned k = 0; k < PART_TILE_PTS / 256; k++) {
-    const size_t i = tile0 + k * 256 + threadIdx.x;
-    if (i < n) {
-      Fr s = load_scalar_regular(scalars, i);
-      for_each_digit(s, sh, [&](unsigned w, int d) {
-        if (d != 0) {
-          const unsigned mag = d < 0 ? (unsigned)(-d) : (unsigned)d;
-          atomicAdd(&cnt[(w * sh.key_stride + (mag - 1)) >> part_log], 1u);
-        }
-      });
-    }
-  }
-  __syncthreads();
-  // reserve one run per partition in the partition-ordered scratch array
-  for (unsigned p = threadIdx.x; p < nparts; p += blockDim.x) {
-    const unsigned c = cnt[p];
-    base[p] = c ? atomicAdd(&part_cursor[p], c) : 0u;
-    cnt[p] = 0;
-  }
-  __syncthreads();
-  // pass 2: emit (bucket, entry) records into the reserved runs
-  for (unsigned k = 0; k < PART_TILE_PTS / 256; k++) {
-    const size_t i = tile0 + k * 256 + threadIdx.x;
-    if (i < n) {
-      Fr s = load_scalar_regular(scalars, i);
-      for_each_digit(s, sh, [&](unsigned w, int d) {
-        if (d != 0) {
-          const unsigned mag = d < 0 ? (unsigned)(-d) : (unsigned)d;
-          const unsigned key = w * sh.key_stride + (mag - 1);
-          const unsigned p = key >> part_log;
-          const unsigned slot = atomicAdd(&cnt[p], 1u);
-          tmp[base[p] + slot] = make_uint2(key, (w * sh.tab_stride + sh.first + (unsigned)i) | (d < 0 ? 0x80000000u : 0u));
-        }
-      });
-    }
-  }
-}
-
-// one CTA per partition: per-bucket cursors live in shared memory
-__global__ void __launch_bounds__(1024) msm_scatter_local_kernel(const uint2* __restrict__ tmp, const unsigned* __restrict__ starts,
-                                                                 unsigned part_log, unsigned nbuckets,
-                                                                 unsigned* __restrict__ sorted) {
-  extern __shared__ unsigned cur[];
-  const unsigned psize = 1u << part_log;
-  const unsigned b0 = blockIdx.x << part_log;
-  const unsigned b1 = b0 + psize < nbuckets ? b0 + psize : nbuckets;
-  for (unsigned b = threadIdx.x; b < b1 - b0; b += blockDim.x) cur[b] = starts[b0 + b];
-  __syncthreads();
-  const unsigned lo = starts[b0], hi = starts[b1];
-  for (unsigned j = lo + threadIdx.x; j < hi; j += blockDim.x) {
-    const uint2 rec = tmp[j];
-    const unsigned pos = atomicAdd(&cur[rec.x - b0], 1u);
-    sorted[pos] = rec.y;
-  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -562,11 +491,6 @@ __global__ void iota_u32_kernel(unsigned* __restrict__ dst, size_t n) {
   if (i < n) dst[i] = (unsigned)i;
 }
 
-__global__ void copy_strided_u32_kernel(const unsigned* __restrict__ src, unsigned* __restrict__ dst, unsigned n, unsigned shift) {
-  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = src[(size_t)i << shift];
-}
-
 __global__ void copy_u32_kernel(const unsigned* __restrict__ src, unsigned* __restrict__ dst, size_t n) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i < n) dst[i] = src[i];
@@ -870,31 +794,7 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
                                                                (const unsigned*)iota, order, (int)nbuckets, 0, 32, st));
     ctx->launches += 4;
   }
-  if (total >= ((size_t)1 << 18) && ctx->msm_flat_scatter == 2) {
-    // two-level scatter (large problems): partition, then shared-memory counting sort per partition
-    PhaseTimer pt(ctx, PH_MSM_SCATTER, st);
-    unsigned lgb = 0;
-    while ((1u << lgb) < nbuckets) lgb++;
-    unsigned part_log = lgb > 7 ? lgb - 7 : 0;
-    if (part_log > 14) part_log = 14;
-    if (part_log < 8) part_log = 8;
-    while (((nbuckets + (1u << part_log) - 1) >> part_log) > (unsigned)MAX_PARTS) part_log++;
-    const unsigned nparts = (nbuckets + (1u << part_log) - 1) >> part_log;
-    B200ZK_TRY(ensure(ctx, ws.msm_part, total * sizeof(uint2) + (size_t)MAX_PARTS * 4, st));
-    uint2* tmp2 = (uint2*)ws.msm_part.p;
-    unsigned* part_cursor = (unsigned*)((char*)ws.msm_part.p + total * sizeof(uint2));
-    // partition p owns sorted[starts[p << part_log] ...): its cursor starts there
-    copy_strided_u32_kernel<<<(nparts + 255) / 256, 256, 0, st>>>(starts, part_cursor, nparts, part_log);
-    B200ZK_LAUNCH_CHECK(ctx, "copy_strided_u32_kernel");
-    const unsigned tiles = (unsigned)((n + PART_TILE_PTS - 1) / PART_TILE_PTS);
-    msm_partition_kernel<<<tiles, 256, 0, st>>>((const uint4*)scalars_dev, n, sh, part_log, nparts, part_cursor, tmp2);
-    B200ZK_LAUNCH_CHECK(ctx, "msm_partition_kernel");
-    const size_t shm = (size_t)4 << part_log;
-    if (shm > 48 * 1024)
-      B200ZK_CUDA(ctx, cudaFuncSetAttribute(msm_scatter_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-    msm_scatter_local_kernel<<<nparts, 1024, shm, st>>>(tmp2, starts, part_log, nbuckets, sorted);
-    B200ZK_LAUNCH_CHECK(ctx, "msm_scatter_local_kernel");
-  } else {
+  {
     PhaseTimer pt(ctx, PH_MSM_SCATTER, st);
     unsigned blocks = (unsigned)((n + 255) / 256);
     if (sh.W <= 13)

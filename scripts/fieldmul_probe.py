@@ -15,11 +15,12 @@ n = 1 << lg
 srs = zk.SRS.NewSRS(n, zkp.fr_to_mont([12345678901234567890]), ctx).precompute()
 sc = torch.from_numpy(images(n, 7)).cuda(); torch.cuda.synchronize()
 out = torch.zeros(64, dtype=torch.uint8, device="cuda")
-for _ in range(2): zk.MultiExp(srs, sc, n=n, out=out)
-ctx.profile(True); ctx.profile_read()
-for _ in range(5): zk.MultiExp(srs, sc, n=n, out=out)
-ph = ctx.profile_read(); ctx.profile(False)
-print("msm 2^%d table:" % lg, {k: round(v[0] / 5, 3) for k, v in ph.items() if v[1]}, "sum", round(sum(v[0] for v in ph.values()) / 5, 3))
+for mode in (0,):
+    for _ in range(2): zk.MultiExp(srs, sc, n=n, out=out)
+    ctx.profile(True); ctx.profile_read()
+    for _ in range(5): zk.MultiExp(srs, sc, n=n, out=out)
+    ph = ctx.profile_read(); ctx.profile(False)
+    print("msm 2^%d table, front end %d:" % (lg, mode), {k: round(v[0] / 5, 3) for k, v in ph.items() if v[1]}, "sum", round(sum(v[0] for v in ph.values()) / 5, 3))
 srs.close(); del sc
 a = torch.from_numpy(images(n, 3)).cuda(); torch.cuda.synchronize()
 d = zk.Domain(n, ctx)

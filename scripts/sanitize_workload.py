@@ -52,9 +52,6 @@ if "msm" in parts:
     assert zk.MultiExp(srs, same) == r1
     lib.b200zk_msm_set_small_path(ctx.handle, 1)
     zk.MultiExp(srs, sc[: 100 * 32], n=100)        # tiny path
-    lib.b200zk_msm_set_flat_scatter(ctx.handle, 2)
-    assert zk.MultiExp(srs, sc) == r0              # two-level scatter
-    lib.b200zk_msm_set_flat_scatter(ctx.handle, 0)
     lib.b200zk_msm_set_host_chunks(ctx.handle, 3)
     assert zk.MultiExp(srs, sc) == r0              # chunked host path (copy stream + partial sums)
     lib.b200zk_msm_set_host_chunks(ctx.handle, 0)

@@ -266,9 +266,8 @@ def test_srs_compressed_roundtrip_matches_gnark_encoding(ctx):
     back.close()
 
 
-def test_flat_and_two_level_scatter_agree(ctx):
-    """both counting-sort variants (global returning atomics / partition + shared-memory cursors), classic and table"""
-    lib = zk.load()
+def test_scatter_with_zero_digits_and_long_runs(ctx):
+    """the counting-sort front end on skewed scalars (zero digits, one very long run), classic windows and table"""
     n = 1 << 17
     pts = structured(n)
     sc = cref.random_fr(n, 0xB2000001 + 99)
@@ -277,10 +276,15 @@ def test_flat_and_two_level_scatter_agree(ctx):
     for table in (False, True):
         if table:
             srs.precompute()
-        for flat in (2, 0):
-            lib.b200zk_msm_set_flat_scatter(ctx.handle, flat)
+        for flat in (0,):
             assert zk.MultiExp(srs, sc) == want, (table, flat)
-    lib.b200zk_msm_set_flat_scatter(ctx.handle, 0)
+            # skewed scalars: half of them zero (zero digits -> the sentinel bucket of the sort-based front end), a
+            # quarter all-equal (one very long run)
+            sk = sc.copy().reshape(n, 32)
+            sk[::2] = 0
+            sk[1::4] = sk[1]
+            sk = sk.reshape(-1)
+            assert zk.MultiExp(srs, sk) == cref.msm(pts, sk, n, nthreads=cref.ncores()), (table, flat, "skewed")
     srs.close()
 
 
