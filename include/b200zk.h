@@ -119,8 +119,8 @@ int b200zk_bases_download_compressed(b200zk_ctx* ctx, const b200zk_bases* bases,
 /* copy bases[first .. first+n) back to the host (64 B each), e.g. to serialise a generated SRS */
 int b200zk_bases_download(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first, size_t n, void* out_host);
 /* One-time precomputation for static bases (the SRS does not change between commitments): stores the window
- * multiples 2^(c*j) * P_i, j < ceil(255/c), next to the bases (W times the memory).  MSMs over at least 1/16 of the
- * bases then use a single shared bucket set: no per-window reduction, no Horner tail, c ~ log2(n) - 2.
+ * multiples 2^(c*j) * P_i, j < ceil(255/c), next to the bases (W times the memory).  MSMs over these bases then use a
+ * single shared bucket set: no per-window reduction, no Horner tail, c ~ log2(n) - 2.
  * c = 0 chooses c from the number of bases; 10 <= c <= 23 otherwise.  Results are unchanged (canonical affine). */
 int b200zk_bases_precompute(b200zk_ctx* ctx, b200zk_bases* bases, int c);
 void b200zk_bases_free(b200zk_ctx* ctx, b200zk_bases* bases);

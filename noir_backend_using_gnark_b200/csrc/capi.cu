@@ -310,7 +310,7 @@ int b200zk_msm_g1_dev(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_b
 // host scalars -> result left on the device (stage + 0: affine, or extended-Jacobian partial), on the context stream
 static int msm_host_scalars(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const void* scalars_host, size_t n,
                             int out_kind, char** result_dev) {
-  const size_t head = 128 + 8 * 128;  // result + up to 8 partial sums
+  const size_t head = 256;  // the result (affine or extended-Jacobian)
   const size_t bytes = n * 32 + head;
   B200ZK_TRY(ensure(ctx, ctx->stage, bytes));
   char* stage = (char*)ctx->stage.p;
@@ -346,13 +346,16 @@ static int msm_host_scalars(b200zk_ctx* ctx, const b200zk_bases* bases, size_t f
     return B200ZK_OK;
   };
   B200ZK_TRY(copy_chunk(0));
+  // every chunk is scattered and accumulated into the SAME buckets (shape of the whole MSM); the bucket reduction and
+  // the normalisation run once, after the last chunk
   for (unsigned i = 0; i < chunks; i++) {
     if (i + 1 < chunks) B200ZK_TRY(copy_chunk(i + 1));
     const size_t first = bound[i], cnt = bound[i + 1] - first;
     B200ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[i], 0));
-    B200ZK_TRY(msm_run(ctx, bases, first_base + first, sc + first * 32, cnt, stage + 128 + 128 * i, 1));
+    const int part = i == 0 ? MSM_PART_FIRST : (i + 1 == chunks ? MSM_PART_LAST : MSM_PART_MORE);
+    B200ZK_TRY(msm_run(ctx, bases, first_base + first, sc + first * 32, cnt, stage, out_kind, 0, part, n));
   }
-  return g1_sum_run(ctx, stage + 128, chunks, stage, out_kind);
+  return B200ZK_OK;
 }
 
 int b200zk_msm_g1(b200zk_ctx* ctx, const b200zk_bases* bases, const void* scalars_host, size_t n,

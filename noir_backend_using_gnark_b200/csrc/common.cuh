@@ -174,8 +174,10 @@ int bit_reverse_run(b200zk_ctx* ctx, void* a_dev, unsigned log2n);
 void ntt_free_domains(b200zk_ctx* ctx);
 int ntt_prepare(b200zk_ctx* ctx, unsigned log2n);  // builds the twiddle / coset tables of a domain if missing
 // lane: which workspace / stream of the context runs it (0 = the context stream)
+// part / shape_n: one MSM fed in several chunks (see msm.cu); MSM_PART_ALL = the whole MSM in one call
+enum { MSM_PART_ALL = 0, MSM_PART_FIRST = 1, MSM_PART_MORE = 2, MSM_PART_LAST = 3 };
 int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const void* scalars_dev, size_t n,
-            void* out_dev, int out_kind, int lane = 0);
+            void* out_dev, int out_kind, int lane = 0, int part = MSM_PART_ALL, size_t shape_n = 0);
 int msm_precompute_run(b200zk_ctx* ctx, b200zk_bases* bases, int c);
 unsigned msm_window_count(const b200zk_ctx* ctx, const b200zk_bases* bases, size_t n);
 // out_kind 0: canonical affine (64 B); 1: extended-Jacobian sum (128 B)

@@ -48,6 +48,7 @@ struct MsmShape {
   unsigned tab_stride;  // table index = w * tab_stride + point index   (0 or table row length)
   unsigned first;       // index of the first base used
   unsigned big_len;     // runs longer than this go to the cooperative path
+  unsigned resume;      // 1: the buckets hold the partial sums of an earlier chunk of the same MSM (host-scalar chunks)
   // window w covers scalar bits [wstart[w], wstart[w+1]); classic mode: uniform c-bit windows.  Table mode splits the
   // 255 bits (254 scalar bits + one spare bit that absorbs the last carry) EVENLY over W windows, so the top window
   // is as wide as the others instead of holding only 254 - c*(W-1) bits (which funnels n entries into a few buckets)
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(128, 4) msm_accumulate_kernel(const void* __re
   if (tid >= nbuckets) return;
   const unsigned b = order[tid];
   unsigned lo = starts[b], hi = starts[b + 1];
-  G1XYZZ acc = g1_xyzz_inf();
+  G1XYZZ acc = sh.resume ? g1_load_xyzz(buckets, b) : g1_xyzz_inf();
   if (hi - lo <= sh.big_len && hi > lo) {
     // software pipeline of the random 64-byte gathers: the point for step j+1 is loaded into registers while step j
     // adds, and the line for step j+3 is pulled into L2 (the window table is far larger than L2 and the TLB reach)
@@ -312,7 +313,7 @@ __global__ void __launch_bounds__(BIG_THREADS) msm_big_reduce_kernel(const unsig
                                                                      const unsigned* __restrict__ big_bucket,
                                                                      const unsigned* __restrict__ big_first_chunk,
                                                                      unsigned cap, const void* __restrict__ partials,
-                                                                     void* __restrict__ buckets) {
+                                                                     void* __restrict__ buckets, unsigned resume) {
   extern __shared__ uint4 big_smem[];
   G1XYZZ* sh_pts = reinterpret_cast<G1XYZZ*>(big_smem);
   const unsigned nbig = plan->nbig < cap ? plan->nbig : cap;
@@ -326,7 +327,13 @@ __global__ void __launch_bounds__(BIG_THREADS) msm_big_reduce_kernel(const unsig
       g1_add(acc, q);
     }
     block_reduce_xyzz(acc, sh_pts);
-    if (threadIdx.x == 0) g1_store_xyzz(buckets, b, acc);
+    if (threadIdx.x == 0) {
+      if (resume) {
+        G1XYZZ prev = g1_load_xyzz(buckets, b);  // the accumulate kernel left the earlier chunks' sum untouched
+        g1_add(acc, prev);
+      }
+      g1_store_xyzz(buckets, b, acc);
+    }
   }
 }
 
@@ -650,7 +657,7 @@ int msm_precompute_run(b200zk_ctx* ctx, b200zk_bases* bases, int c_req) {
 
 // number of windows (= bucket additions per point) msm_run uses for n points of these bases; same rule as below
 unsigned msm_window_count(const b200zk_ctx* ctx, const b200zk_bases* bases, size_t n) {
-  if (bases->table && !ctx->forced_window && n * 16 >= bases->n) return bases->tab_W;
+  if (bases->table && !ctx->forced_window) return bases->tab_W;
   unsigned c = ctx->forced_window ? (unsigned)ctx->forced_window : choose_window(n);
   if (c < 6) c = 6;
   if (c > 16) c = 16;
@@ -658,8 +665,15 @@ unsigned msm_window_count(const b200zk_ctx* ctx, const b200zk_bases* bases, size
 }
 
 int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const void* scalars_dev, size_t n,
-            void* out_dev, int out_kind, int lane) {
+            void* out_dev, int out_kind, int lane, int part, size_t shape_n) {
   if (!bases || !out_dev || (n && !scalars_dev) || lane < 0 || lane >= MSM_LANES) return B200ZK_ERR_BAD_ARG;
+  // part: one MSM fed in several chunks of points (host scalars arriving over PCIe) — MSM_PART_FIRST / MSM_PART_MORE stop
+  // after the bucket accumulation, MSM_PART_MORE / MSM_PART_LAST continue from the buckets of the previous chunk; all
+  // chunks take their shape (windows, buckets) from shape_n = the size of the whole MSM
+  const bool resume = part == MSM_PART_MORE || part == MSM_PART_LAST;
+  const bool stop_after_accumulate = part == MSM_PART_FIRST || part == MSM_PART_MORE;
+  if (part == MSM_PART_ALL) shape_n = n;
+  if (shape_n < n) return B200ZK_ERR_BAD_ARG;
   MsmWorkspace& ws = ctx->ws[lane];
   if (first_base > bases->n || n > bases->n - first_base) return B200ZK_ERR_BAD_ARG;
   if (n >= ((size_t)1 << 31)) return B200ZK_ERR_UNSUPPORTED;
@@ -671,7 +685,8 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
   }
   MsmShape sh;
   memset(&sh, 0, sizeof(sh));
-  if (bases->table && !ctx->forced_window && !ctx->msm_no_tiny && n * (size_t)bases->tab_W <= TINY_MAX_TERMS) {
+  if (part == MSM_PART_ALL && bases->table && !ctx->forced_window && !ctx->msm_no_tiny &&
+      n * (size_t)bases->tab_W <= TINY_MAX_TERMS) {
     // small problem: one thread per (point, window) term of the table, two launches
     const bool head = bases->small_table && first_base + n <= bases->small_n;  // narrow windows: shorter digit chains
     const void* tiny_table = head ? bases->small_table : bases->table;
@@ -691,7 +706,10 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
     B200ZK_LAUNCH_CHECK(ctx, "msm_tiny_final_kernel");
     return B200ZK_OK;
   }
-  const bool use_table = bases->table && !ctx->forced_window && n * 16 >= bases->n;
+  // a table is used whenever there is one: even for an MSM over a small part of a large SRS the fixed cost of reducing the
+  // table's single bucket set (0.8 ms at 2^19 buckets) is below the classic path's per-window reductions plus its Horner
+  // tail of W*c dependent doublings on one thread (1.1 ms)
+  const bool use_table = bases->table && !ctx->forced_window;
   const void* base_ptr;
   if (use_table) {
     sh.c = bases->tab_c;
@@ -703,7 +721,7 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
     memcpy(sh.wstart, bases->tab_wstart, sizeof(sh.wstart));
     base_ptr = bases->table;
   } else {
-    sh.c = ctx->forced_window ? (unsigned)ctx->forced_window : choose_window(n);
+    sh.c = ctx->forced_window ? (unsigned)ctx->forced_window : choose_window(shape_n);
     if (sh.c < 6) sh.c = 6;
     if (sh.c > 16) sh.c = 16;
     sh.W = (255 + sh.c - 1) / sh.c;  // c*W >= 255: the top window never produces a carry
@@ -715,6 +733,7 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
     base_ptr = bases->dev;
   }
   sh.first = (unsigned)first_base;
+  sh.resume = resume ? 1u : 0u;
   const size_t total = n * sh.W;
   if (total >= ((size_t)1 << 32) || sh.W > MAX_WINDOWS) return B200ZK_ERR_UNSUPPORTED;
   const unsigned nbuckets = sh.nsets * sh.B;
@@ -822,9 +841,10 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
                                                                        chunk_idx, ws.msm_big.p);
     B200ZK_LAUNCH_CHECK(ctx, "msm_big_accumulate_kernel");
     msm_big_reduce_kernel<<<ctx->sm_count, BIG_THREADS, shm, st>>>(starts, plan, big_bucket, big_first, big_cap,
-                                                                   ws.msm_big.p, ws.msm_buckets.p);
+                                                                   ws.msm_big.p, ws.msm_buckets.p, sh.resume);
     B200ZK_LAUNCH_CHECK(ctx, "msm_big_reduce_kernel");
   }
+  if (stop_after_accumulate) return B200ZK_OK;  // the next chunk of this MSM continues from ws.msm_buckets
   {
     PhaseTimer pt(ctx, PH_MSM_REDUCE, st);
     const unsigned tot1 = sh.nsets * chunks_per_set;
