@@ -151,6 +151,11 @@ int b200zk_msm_set_reduce_chunk(b200zk_ctx* ctx, int chunk_log);
 /* tests: with a window table, MSMs of up to 2^17 (point, window) terms skip the bucket pipeline (one thread per term,
  * two launches: the sizes of the reference's own test circuits); 0 forces the bucket pipeline there too, 1 = default */
 int b200zk_msm_set_small_path(b200zk_ctx* ctx, int on);
+/* Batched-affine pair rounds of the bucket accumulation: the counting sort pads every bucket's run to a multiple of
+ * 2^rounds entries and `rounds` passes of out[o] = in[2o] + in[2o+1] (affine additions, one inversion per lane per
+ * batch: 5M + 1S per addition instead of 8M + 2S) pre-sum the runs before the extended-Jacobian walk.
+ * -1 = choose from the size (default), 0 = off, 1..6 = forced (tests / tuning).  The result does not depend on it. */
+int b200zk_msm_set_pair_rounds(b200zk_ctx* ctx, int rounds);
 /* force the Pippenger window size (0 = choose from n); for tests and tuning */
 int b200zk_msm_set_window(b200zk_ctx* ctx, int c);
 /* measurement: the number of windows (= bucket additions per point) an MSM of n points of these bases will use

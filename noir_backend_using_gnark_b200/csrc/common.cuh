@@ -47,7 +47,7 @@ namespace b200zk {
 static constexpr int MSM_LANES = 3;
 struct MsmWorkspace {
   DeviceBuf msm_digits, msm_sorted, msm_counts, msm_starts, msm_cursor, msm_buckets, msm_tmp, msm_small, msm_scan_tmp,
-      msm_big;
+      msm_big, msm_pairs;
   cudaStream_t stream = nullptr;   // lane 0: the context stream
   cudaEvent_t done = nullptr;      // recorded after the lane's last MSM (lanes > 0)
 };
@@ -80,6 +80,8 @@ struct b200zk_ctx {
   bool lane_pending = false;     // a forked commitment is in flight on MSM lane 1
   int msm_single_lane = 0;       // tests / tuning: the prover's commitment rounds run one MSM after the other
   int msm_no_tiny = 0;           // tests: force the bucket pipeline also for small table-mode MSMs
+  int msm_pair_rounds = -1;      // batched-affine pair rounds before the bucket walk: -1 = from the size, 0 = off, r = forced
+  int msm_pair_kmax = 0;         // tuning: additions per inversion per lane (0 = default)
   uint64_t launches = 0;
   char cuda_err[256] = {0};
   int forced_window = 0;

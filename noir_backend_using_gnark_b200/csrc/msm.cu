@@ -183,33 +183,182 @@ __device__ __forceinline__ G1Affine load_signed(const void* bases, unsigned entr
   return p;
 }
 
+// Element j of a bucket's run.  Gathered: the sorted entry names a (signed) point of the bases / window table.
+// LINEAR: the run was pre-summed by the pair rounds below and lies as affine points in a staging buffer; run bounds are
+// the padded bucket offsets shifted down by the number of rounds.
+template <bool LINEAR>
+__device__ __forceinline__ G1Affine run_point(const void* src, const unsigned* __restrict__ sorted, unsigned j) {
+  if (LINEAR) return g1_load_affine(src, j);
+  return load_signed(src, sorted[j]);
+}
+
 // Threads take buckets in order of decreasing run length (`order`), so the 32 runs of a warp have (almost) the same
 // length and the longest runs start first: no lane idles while its neighbours finish.
-__global__ void __launch_bounds__(128, 4) msm_accumulate_kernel(const void* __restrict__ bases, const unsigned* __restrict__ starts,
+template <bool LINEAR>
+__global__ void __launch_bounds__(128, 4) msm_accumulate_kernel(const void* __restrict__ src, const unsigned* __restrict__ starts,
                                                              const unsigned* __restrict__ sorted,
-                                                             const unsigned* __restrict__ order, MsmShape sh,
+                                                             const unsigned* __restrict__ order, MsmShape sh, unsigned shift,
                                                              unsigned nbuckets, void* __restrict__ buckets) {
   unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= nbuckets) return;
   const unsigned b = order[tid];
-  unsigned lo = starts[b], hi = starts[b + 1];
+  unsigned lo = starts[b] >> shift, hi = starts[b + 1] >> shift;
   G1XYZZ acc = sh.resume ? g1_load_xyzz(buckets, b) : g1_xyzz_inf();
   if (hi - lo <= sh.big_len && hi > lo) {
     // software pipeline of the random 64-byte gathers: the point for step j+1 is loaded into registers while step j
     // adds, and the line for step j+3 is pulled into L2 (the window table is far larger than L2 and the TLB reach)
-    G1Affine cur = load_signed(bases, sorted[lo]);
+    G1Affine cur = run_point<LINEAR>(src, sorted, lo);
     for (unsigned j = lo + 1; j < hi; j++) {
-      if (j + 2 < hi) {
-        const char* ahead = reinterpret_cast<const char*>(bases) + (size_t)(sorted[j + 2] & 0x7fffffffu) * 64;
+      if (!LINEAR && j + 2 < hi) {
+        const char* ahead = reinterpret_cast<const char*>(src) + (size_t)(sorted[j + 2] & 0x7fffffffu) * 64;
         asm volatile("prefetch.global.L2 [%0];" ::"l"(ahead));
       }
-      G1Affine nxt = load_signed(bases, sorted[j]);
+      G1Affine nxt = run_point<LINEAR>(src, sorted, j);
       g1_add_mixed(acc, cur);
       cur = nxt;
     }
     g1_add_mixed(acc, cur);
   }
   g1_store_xyzz(buckets, b, acc);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 4a. pair rounds (batched affine additions).  The counting sort pads every bucket's run to a multiple of 2^R entries
+//     (pad entries = infinity), so R rounds of  out[o] = in[2o] + in[2o+1]  over the whole entry array pre-sum each run
+//     to 1/2^R of its length without any bucket bookkeeping.  An affine addition needs 1/(x2-x1): every lane batches
+//     the K denominators of its K slots with Montgomery's trick (forward pass: running product, parked in the output
+//     slot; ONE inversion per lane; backward pass: 1/d_k, lambda, the sum) = 5 multiplications + 1 squaring per
+//     addition + one Fermat inversion per K additions, against 8 + 2 for the extended-Jacobian mixed addition.
+//     Lanes of a warp take consecutive slots (slot = base + 32k + lane): the entry pairs, the staged points of later
+//     rounds, the parked products and the sums are all warp-contiguous.
+// ---------------------------------------------------------------------------------------------------
+static constexpr unsigned PAD_ENTRY = 0xffffffffu;   // never a table index: W*n < 2^31
+static constexpr unsigned PAIR_THREADS = 128;
+static constexpr unsigned PAIR_KMAX = 512;
+enum { PAIR_ADD = 0, PAIR_DBL = 1, PAIR_TAKE_A = 2, PAIR_TAKE_B = 3, PAIR_INF = 4 };
+
+__global__ void msm_pad_counts_kernel(const unsigned* __restrict__ counts, unsigned nbuckets, unsigned mask,
+                                      unsigned* __restrict__ padded) {
+  unsigned b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > nbuckets) return;
+  padded[b] = b < nbuckets ? (counts[b] + mask) & ~mask : 0u;
+}
+
+__global__ void msm_pad_fill_kernel(const unsigned* __restrict__ starts, const unsigned* __restrict__ counts,
+                                    unsigned nbuckets, unsigned* __restrict__ sorted) {
+  unsigned b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nbuckets) return;
+  for (unsigned j = starts[b] + counts[b]; j < starts[b + 1]; j++) sorted[j] = PAD_ENTRY;
+}
+
+__device__ __forceinline__ G1Affine load_entry(const void* bases, unsigned entry) {
+  if (entry == PAD_ENTRY) {
+    G1Affine p;
+    p.x = fe_zero<FpParams>();
+    p.y = fe_zero<FpParams>();
+    return p;
+  }
+  return load_signed(bases, entry);
+}
+
+// denominator of the chord / tangent slope of a + b (1 when the sum needs none), and which formula applies
+__device__ __forceinline__ int pair_classify(const G1Affine& a, const G1Affine& b, Fp& d) {
+  const bool ia = g1_is_inf(a), ib = g1_is_inf(b);
+  d = fe_one<FpParams>();
+  if (ia || ib) return ia ? (ib ? PAIR_INF : PAIR_TAKE_B) : PAIR_TAKE_A;
+  const Fp dx = fe_sub(b.x, a.x);
+  if (fe_is_zero(dx)) {
+    if (!fe_eq(a.y, b.y)) return PAIR_INF;   // b = -a
+    d = fe_dbl(a.y);                          // no 2-torsion on this curve: y != 0
+    return PAIR_DBL;
+  }
+  d = dx;
+  return PAIR_ADD;
+}
+
+template <bool FIRST>
+__device__ __forceinline__ void pair_load(const void* __restrict__ src, const unsigned* __restrict__ sorted, size_t o,
+                                          G1Affine& a, G1Affine& b) {
+  if (FIRST) {
+    const uint2 e = __ldg(reinterpret_cast<const uint2*>(sorted) + o);
+    a = load_entry(src, e.x);
+    b = load_entry(src, e.y);
+  } else {
+    a = g1_load_affine(src, 2 * o);
+    b = g1_load_affine(src, 2 * o + 1);
+  }
+}
+
+// FIRST: src = bases / window table, gathered through the sorted entries; otherwise src = the previous round's sums.
+// total_ptr -> padded number of sorted entries (device-side: the host never learns it); this round has total >> round slots.
+template <bool FIRST>
+__global__ void __launch_bounds__(PAIR_THREADS, 4) msm_pair_kernel(const void* __restrict__ src,
+                                                                   const unsigned* __restrict__ sorted,
+                                                                   const unsigned* __restrict__ total_ptr, unsigned round,
+                                                                   unsigned K, void* __restrict__ dst) {
+  const size_t nslots = (size_t)(*total_ptr >> round);
+  const size_t warp = ((size_t)blockIdx.x * PAIR_THREADS + threadIdx.x) >> 5;
+  const size_t base = warp * K * 32 + (threadIdx.x & 31);   // slot of step k = base + 32 k
+  if (base >= nslots) return;
+  const size_t avail = (nslots - base + 31) / 32;
+  const unsigned steps = avail < K ? (unsigned)avail : K;
+  char* out = reinterpret_cast<char*>(dst);
+  // forward: park the product of the earlier denominators in the slot, extend it by this slot's
+  Fp acc = fe_one<FpParams>();
+  {
+    G1Affine a, b;
+    pair_load<FIRST>(src, sorted, base, a, b);
+    for (unsigned k = 0; k < steps; k++) {
+      const size_t o = base + (size_t)k * 32;
+      G1Affine na = a, nb = b;
+      if (k + 1 < steps) pair_load<FIRST>(src, sorted, o + 32, na, nb);   // in flight during the product below
+      Fp d;
+      pair_classify(a, b, d);
+      fe_store(out + o * 64, acc);
+      acc = fe_mul(acc, d);
+      a = na;
+      b = nb;
+    }
+  }
+  Fp inv = fe_inv(acc);   // all lanes invert together; no denominator is zero
+  {
+    G1Affine a, b;
+    pair_load<FIRST>(src, sorted, base + (size_t)(steps - 1) * 32, a, b);
+    for (unsigned k = steps; k-- > 0;) {
+      const size_t o = base + (size_t)k * 32;
+      G1Affine na = a, nb = b;
+      if (k > 0) pair_load<FIRST>(src, sorted, o - 32, na, nb);
+      const Fp pre = fe_load<FpParams>(out + o * 64);
+      Fp d;
+      const int kind = pair_classify(a, b, d);
+      const Fp dinv = fe_mul(inv, pre);   // 1 / d_k
+      inv = fe_mul(inv, d);               // 1 / (d_0 ... d_{k-1})
+      G1Affine r;
+      if (kind <= PAIR_DBL) {
+        Fp num, x2 = b.x;
+        if (kind == PAIR_DBL) {
+          const Fp xx = fe_sqr(a.x);
+          num = fe_add(fe_dbl(xx), xx);
+          x2 = a.x;
+        } else {
+          num = fe_sub(b.y, a.y);
+        }
+        const Fp lam = fe_mul(num, dinv);
+        r.x = fe_sub(fe_sub(fe_sqr(lam), a.x), x2);
+        r.y = fe_sub(fe_mul(lam, fe_sub(a.x, r.x)), a.y);
+      } else if (kind == PAIR_TAKE_A) {
+        r = a;
+      } else if (kind == PAIR_TAKE_B) {
+        r = b;
+      } else {
+        r.x = fe_zero<FpParams>();
+        r.y = fe_zero<FpParams>();
+      }
+      g1_store_affine(dst, o, r);
+      a = na;
+      b = nb;
+    }
+  }
 }
 
 // ---- long runs: list them, split over CTAs, reduce --------------------------------------------------
@@ -219,12 +368,12 @@ struct BigPlan {
 };
 
 // every long run is cut into BIG_CHUNK-entry chunks; chunk descriptors are (bucket, index within the run)
-__global__ void msm_big_list_kernel(const unsigned* __restrict__ starts, unsigned nbuckets, MsmShape sh, BigPlan* plan,
-                                    unsigned* __restrict__ big_bucket, unsigned* __restrict__ big_first_chunk,
+__global__ void msm_big_list_kernel(const unsigned* __restrict__ starts, unsigned nbuckets, MsmShape sh, unsigned shift,
+                                    BigPlan* plan, unsigned* __restrict__ big_bucket, unsigned* __restrict__ big_first_chunk,
                                     unsigned cap, unsigned* __restrict__ chunk_bucket, unsigned* __restrict__ chunk_idx) {
   unsigned b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nbuckets) return;
-  unsigned len = starts[b + 1] - starts[b];
+  unsigned len = (starts[b + 1] >> shift) - (starts[b] >> shift);
   if (len > sh.big_len) {
     unsigned chunks = (len + BIG_CHUNK - 1) / BIG_CHUNK;
     unsigned slot = atomicAdd(&plan->nbig, 1u);
@@ -276,9 +425,10 @@ __device__ __forceinline__ G1XYZZ warp_sum_xyzz(G1XYZZ v) {
 
 // grid-stride over chunk descriptors: one WARP sums one chunk of a long run (lane-serial mixed additions, then a
 // warp-shuffle tree: 5 full additions of overhead per chunk instead of a shared-memory tree per CTA)
+template <bool LINEAR>
 __global__ void __launch_bounds__(BIG_THREADS) msm_big_accumulate_kernel(const void* __restrict__ bases,
                                                                          const unsigned* __restrict__ starts,
-                                                                         const unsigned* __restrict__ sorted,
+                                                                         const unsigned* __restrict__ sorted, unsigned shift,
                                                                          const BigPlan* __restrict__ plan,
                                                                          const unsigned* __restrict__ chunk_bucket,
                                                                          const unsigned* __restrict__ chunk_idx,
@@ -288,15 +438,15 @@ __global__ void __launch_bounds__(BIG_THREADS) msm_big_accumulate_kernel(const v
   const unsigned warps_per_cta = BIG_THREADS / 32;
   for (unsigned item = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); item < nchunks; item += gridDim.x * warps_per_cta) {
     const unsigned b = chunk_bucket[item];
-    const unsigned lo = starts[b], hi = starts[b + 1];
+    const unsigned lo = starts[b] >> shift, hi = starts[b + 1] >> shift;
     unsigned clo = lo + chunk_idx[item] * BIG_CHUNK;
     unsigned chi = clo + BIG_CHUNK < hi ? clo + BIG_CHUNK : hi;
     G1XYZZ acc = g1_xyzz_inf();
     unsigned j = clo + lane;
     if (j < chi) {
-      G1Affine cur = load_signed(bases, sorted[j]);
+      G1Affine cur = run_point<LINEAR>(bases, sorted, j);
       for (j += 32; j < chi; j += 32) {
-        G1Affine nxt = load_signed(bases, sorted[j]);  // in flight while the addition below runs
+        G1Affine nxt = run_point<LINEAR>(bases, sorted, j);  // in flight while the addition below runs
         g1_add_mixed(acc, cur);
         cur = nxt;
       }
@@ -313,13 +463,13 @@ __global__ void __launch_bounds__(BIG_THREADS) msm_big_reduce_kernel(const unsig
                                                                      const unsigned* __restrict__ big_bucket,
                                                                      const unsigned* __restrict__ big_first_chunk,
                                                                      unsigned cap, const void* __restrict__ partials,
-                                                                     void* __restrict__ buckets, unsigned resume) {
+                                                                     void* __restrict__ buckets, unsigned resume, unsigned shift) {
   extern __shared__ uint4 big_smem[];
   G1XYZZ* sh_pts = reinterpret_cast<G1XYZZ*>(big_smem);
   const unsigned nbig = plan->nbig < cap ? plan->nbig : cap;
   for (unsigned slot = blockIdx.x; slot < nbig; slot += gridDim.x) {
     const unsigned b = big_bucket[slot];
-    const unsigned len = starts[b + 1] - starts[b];
+    const unsigned len = (starts[b + 1] >> shift) - (starts[b] >> shift);
     const unsigned chunks = (len + BIG_CHUNK - 1) / BIG_CHUNK;
     G1XYZZ acc = g1_xyzz_inf();
     for (unsigned ch = threadIdx.x; ch < chunks; ch += BIG_THREADS) {
@@ -655,6 +805,19 @@ int msm_precompute_run(b200zk_ctx* ctx, b200zk_bases* bases, int c_req) {
   return B200ZK_OK;
 }
 
+// Number of pair rounds for an MSM with `total` (point, window) entries in `nbuckets` buckets.  Padding a run to a
+// multiple of 2^R costs (2^R - 1)/2 infinity entries per bucket (ctx->msm_pair_rounds: -1 automatic, 0 off, r forced).
+static unsigned pair_rounds(const b200zk_ctx* ctx, size_t total, unsigned nbuckets) {
+  if (total + (size_t)nbuckets * 63 >= ((size_t)1 << 32)) return 0;   // slot arithmetic is 32-bit on the device
+  if (ctx->msm_pair_rounds >= 0) return (unsigned)(ctx->msm_pair_rounds > 6 ? 6 : ctx->msm_pair_rounds);
+  // Measured on B200 (profiles/r02_batch_affine.md): the rounds are bit-exact but SLOWER than letting the extended-Jacobian
+  // walk do everything (2^24 points: 35.5 ms with 3 rounds against 31.2 ms) — the walk needs 64 B of HBM per 9.5
+  // multiplications, a pair round 320-670 B per 6.3, and the first round's gathers are fetched twice at 128-byte
+  // granularity (60 GB read for 104 M additions).  Automatic therefore means off; the path stays for other parts / sizes.
+  (void)nbuckets;
+  return 0;
+}
+
 // number of windows (= bucket additions per point) msm_run uses for n points of these bases; same rule as below
 unsigned msm_window_count(const b200zk_ctx* ctx, const b200zk_bases* bases, size_t n) {
   if (bases->table && !ctx->forced_window) return bases->tab_W;
@@ -737,8 +900,12 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
   const size_t total = n * sh.W;
   if (total >= ((size_t)1 << 32) || sh.W > MAX_WINDOWS) return B200ZK_ERR_UNSUPPORTED;
   const unsigned nbuckets = sh.nsets * sh.B;
+  // pair rounds (batched affine pre-summation of the runs, see msm_pair_kernel): R rounds shorten every run 2^R times
+  const unsigned R = pair_rounds(ctx, total, nbuckets);
+  const unsigned pad = (1u << R) - 1u;
+  const size_t total_bound = total + (size_t)nbuckets * pad;   // upper bound of the padded entry count
   {
-    size_t avg = total / nbuckets;
+    size_t avg = (total / nbuckets) >> R;
     size_t bl = 4 * avg + 256;
     sh.big_len = (unsigned)(bl > 0x7fffffff ? 0x7fffffff : bl);
   }
@@ -754,7 +921,8 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
   const unsigned big_cap = nbuckets / 4 + 16;
   const size_t max_big_chunks = total / BIG_CHUNK + big_cap + 1;
 
-  B200ZK_TRY(ensure(ctx, ws.msm_sorted, total * sizeof(unsigned), st));
+  B200ZK_TRY(ensure(ctx, ws.msm_sorted, total_bound * sizeof(unsigned), st));
+  if (R) B200ZK_TRY(ensure(ctx, ws.msm_pairs, ((total_bound >> 1) + (R > 1 ? (total_bound >> 2) : 0) + 2) * 64, st));
   B200ZK_TRY(ensure(ctx, ws.msm_counts, (size_t)(nbuckets + 1) * 4, st));
   B200ZK_TRY(ensure(ctx, ws.msm_starts, (size_t)(nbuckets + 1) * 4, st));
   B200ZK_TRY(ensure(ctx, ws.msm_cursor, (size_t)(nbuckets + 1) * 4, st));
@@ -801,9 +969,15 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
   }
   {
     PhaseTimer pt(ctx, PH_MSM_SCAN, st);
-    B200ZK_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ws.msm_scan_tmp.p, scan_bytes, counts, starts, (int)(nbuckets + 1), st));
-    ctx->launches++;
     unsigned blocks = (nbuckets + 1 + 255) / 256;
+    const unsigned* lens = counts;
+    if (R) {   // offsets of runs padded to a multiple of 2^R entries (the cursor array doubles as scratch)
+      msm_pad_counts_kernel<<<blocks, 256, 0, st>>>(counts, nbuckets, pad, cursor);
+      B200ZK_LAUNCH_CHECK(ctx, "msm_pad_counts_kernel");
+      lens = cursor;
+    }
+    B200ZK_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ws.msm_scan_tmp.p, scan_bytes, lens, starts, (int)(nbuckets + 1), st));
+    ctx->launches++;
     copy_u32_kernel<<<blocks, 256, 0, st>>>(starts, cursor, nbuckets + 1);
     B200ZK_LAUNCH_CHECK(ctx, "copy_u32_kernel");
     iota_u32_kernel<<<blocks, 256, 0, st>>>(iota, nbuckets);
@@ -823,25 +997,59 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
     else
       msm_scatter_kernel<MAX_WINDOWS><<<blocks, 256, 0, st>>>((const uint4*)scalars_dev, n, sh, cursor, sorted);
     B200ZK_LAUNCH_CHECK(ctx, "msm_scatter_kernel");
+    if (R) {
+      msm_pad_fill_kernel<<<(nbuckets + 255) / 256, 256, 0, st>>>(starts, counts, nbuckets, sorted);
+      B200ZK_LAUNCH_CHECK(ctx, "msm_pad_fill_kernel");
+    }
   }
+  const void* run_src = base_ptr;   // what the run walkers read: the bases / table, or the last pair round's sums
   {
     PhaseTimer pt(ctx, PH_MSM_ACCUMULATE, st);
+    if (R) {
+      // staging: round 1 -> A, round 2: A -> B, round 3: B -> A, ...  (A holds total/2 points, B total/4)
+      char* bufA = (char*)ws.msm_pairs.p;
+      char* bufB = bufA + ((total_bound >> 1) + 1) * 64;
+      const size_t cap_threads = (size_t)ctx->sm_count * 4 * PAIR_THREADS;   // one resident wave
+      const unsigned kmax = ctx->msm_pair_kmax > 0 ? (unsigned)ctx->msm_pair_kmax : PAIR_KMAX;
+      for (unsigned r = 1; r <= R; r++) {
+        const size_t slots = (total_bound >> r) + 1;
+        const size_t waves = (slots + cap_threads * kmax - 1) / (cap_threads * kmax);
+        unsigned K = (unsigned)((slots + cap_threads * waves - 1) / (cap_threads * waves));
+        if (K < 1) K = 1;
+        const size_t warps = (slots + (size_t)K * 32 - 1) / ((size_t)K * 32);
+        const unsigned blocks = (unsigned)((warps * 32 + PAIR_THREADS - 1) / PAIR_THREADS);
+        void* dst = (r & 1) ? bufA : bufB;
+        if (r == 1)
+          msm_pair_kernel<true><<<blocks, PAIR_THREADS, 0, st>>>(base_ptr, sorted, starts + nbuckets, r, K, dst);
+        else
+          msm_pair_kernel<false><<<blocks, PAIR_THREADS, 0, st>>>(run_src, nullptr, starts + nbuckets, r, K, dst);
+        B200ZK_LAUNCH_CHECK(ctx, "msm_pair_kernel");
+        run_src = dst;
+      }
+    }
     unsigned blocks = (nbuckets + 127) / 128;
-    msm_accumulate_kernel<<<blocks, 128, 0, st>>>(base_ptr, starts, sorted, order, sh, nbuckets, ws.msm_buckets.p);
+    if (R)
+      msm_accumulate_kernel<true><<<blocks, 128, 0, st>>>(run_src, starts, sorted, order, sh, R, nbuckets, ws.msm_buckets.p);
+    else
+      msm_accumulate_kernel<false><<<blocks, 128, 0, st>>>(run_src, starts, sorted, order, sh, 0, nbuckets, ws.msm_buckets.p);
     B200ZK_LAUNCH_CHECK(ctx, "msm_accumulate_kernel");
   }
   {
     PhaseTimer pt(ctx, PH_MSM_BIG, st);
     unsigned blocks = (nbuckets + 255) / 256;
-    msm_big_list_kernel<<<blocks, 256, 0, st>>>(starts, nbuckets, sh, plan, big_bucket, big_first, big_cap, chunk_bucket,
+    msm_big_list_kernel<<<blocks, 256, 0, st>>>(starts, nbuckets, sh, R, plan, big_bucket, big_first, big_cap, chunk_bucket,
                                                 chunk_idx);
     B200ZK_LAUNCH_CHECK(ctx, "msm_big_list_kernel");
     const size_t shm = BIG_THREADS * sizeof(G1XYZZ);
-    msm_big_accumulate_kernel<<<ctx->sm_count * 4, BIG_THREADS, 0, st>>>(base_ptr, starts, sorted, plan, chunk_bucket,
-                                                                       chunk_idx, ws.msm_big.p);
+    if (R)
+      msm_big_accumulate_kernel<true><<<ctx->sm_count * 4, BIG_THREADS, 0, st>>>(run_src, starts, sorted, R, plan, chunk_bucket,
+                                                                               chunk_idx, ws.msm_big.p);
+    else
+      msm_big_accumulate_kernel<false><<<ctx->sm_count * 4, BIG_THREADS, 0, st>>>(run_src, starts, sorted, 0, plan,
+                                                                                chunk_bucket, chunk_idx, ws.msm_big.p);
     B200ZK_LAUNCH_CHECK(ctx, "msm_big_accumulate_kernel");
     msm_big_reduce_kernel<<<ctx->sm_count, BIG_THREADS, shm, st>>>(starts, plan, big_bucket, big_first, big_cap,
-                                                                   ws.msm_big.p, ws.msm_buckets.p, sh.resume);
+                                                                   ws.msm_big.p, ws.msm_buckets.p, sh.resume, R);
     B200ZK_LAUNCH_CHECK(ctx, "msm_big_reduce_kernel");
   }
   if (stop_after_accumulate) return B200ZK_OK;  // the next chunk of this MSM continues from ws.msm_buckets

@@ -462,3 +462,133 @@ def test_small_msm_on_the_head_of_a_large_table(ctx):
             assert out.cpu().numpy().tobytes() == want, (first, m)
     finally:
         srs.close()
+
+
+# ---- pair rounds: batched affine pre-summation of the bucket runs (b200zk_msm_set_pair_rounds) ----------------------
+@pytest.fixture
+def pair_rounds(ctx):
+    lib = zk.load()
+
+    def set_rounds(r):
+        assert lib.b200zk_msm_set_pair_rounds(ctx.handle, r) == 0
+
+    yield set_rounds
+    lib.b200zk_msm_set_pair_rounds(ctx.handle, -1)
+    lib.b200zk_msm_set_small_path(ctx.handle, 1)
+    lib.b200zk_msm_set_window(ctx.handle, 0)
+    lib.b200zk_msm_set_host_chunks(ctx.handle, 0)
+
+
+@pytest.mark.parametrize("rounds", [1, 2, 3, 5])
+def test_pair_rounds_special_points_and_scalars(ctx, pair_rounds, rounds):
+    """Infinity among the bases, duplicate points with equal scalars (the tangent case of the affine addition),
+    P + (-P) inside a run, zero / one / r-1 scalars, every window size, with and without the window table."""
+    lib = zk.load()
+    n = 600
+    pts = structured(n).copy()
+    pts[5 * 64 : 6 * 64] = 0
+    pts[9 * 64 : 10 * 64] = pts[8 * 64 : 9 * 64]
+    pts[11 * 64 : 12 * 64] = pts[8 * 64 : 9 * 64]
+    vals = o.random_fr(n, 17)
+    vals[0] = 0
+    vals[1] = 1
+    vals[2] = o.R_MOD - 1
+    vals[3] = (1 << 253) % o.R_MOD
+    vals[8] = vals[9]
+    vals[11] = o.R_MOD - vals[8]                    # -P next to P, P in the same buckets
+    vals[20] = 1 << 15
+    sc = np.frombuffer(o.fr_to_mont_bytes(vals), dtype=np.uint8)
+    srs = zk.SRS(pts, ctx)
+    want = cref.msm(pts, sc, n, nthreads=4)
+    pair_rounds(rounds)
+    lib.b200zk_msm_set_small_path(ctx.handle, 0)
+    for table in (False, True):
+        if table:
+            srs.precompute()
+        for c in (0, 6, 9, 13, 16):
+            lib.b200zk_msm_set_window(ctx.handle, c)
+            assert zk.MultiExp(srs, sc) == want, (table, c)
+        lib.b200zk_msm_set_window(ctx.handle, 0)
+        assert zk.MultiExp(srs, np.zeros(n * 32, dtype=np.uint8)) == b"\0" * 64
+    srs.close()
+
+
+@pytest.mark.parametrize("rounds", [1, 3, 6])
+@pytest.mark.parametrize("kind", ["all_equal", "witness_like", "same_point"])
+def test_pair_rounds_skewed_inputs(ctx, pair_rounds, rounds, kind):
+    """Long runs after the pair rounds still go through the cooperative path (run bounds shifted by the rounds)."""
+    n = 1 << 15
+    pts = structured(n)
+    if kind == "all_equal":
+        v = o.random_fr(1, 5)[0]
+        sc = np.tile(np.frombuffer(o.fr_to_mont_bytes([v]), dtype=np.uint8), n)
+    elif kind == "witness_like":
+        rnd = o.random_fr(n // 4, 6)
+        vals = [0] * (n // 2) + [x % (1 << 16) for x in rnd] + rnd
+        sc = np.frombuffer(o.fr_to_mont_bytes(vals), dtype=np.uint8)
+    else:
+        pts = np.tile(np.frombuffer(gen_point(777), dtype=np.uint8), n)   # every pair is a doubling
+        sc = cref.random_fr(n, 8)
+    srs = zk.SRS(pts, ctx)
+    want = cref.msm(pts, sc, n, nthreads=cref.ncores())
+    pair_rounds(rounds)
+    for c in (0, 8):
+        zk.load().b200zk_msm_set_window(ctx.handle, c)
+        assert zk.MultiExp(srs, sc) == want, (kind, c)
+    zk.load().b200zk_msm_set_window(ctx.handle, 0)
+    srs.precompute()
+    assert zk.MultiExp(srs, sc) == want, (kind, "table")
+    srs.close()
+
+
+@pytest.mark.parametrize("log2n", [16, 18])
+def test_pair_rounds_vs_c_oracle_medium(ctx, pair_rounds, log2n):
+    lib = zk.load()
+    n = (1 << log2n) + 13
+    pts = structured(n)
+    sc = cref.random_fr(n, 0xB2000001)
+    srs = zk.SRS(pts, ctx)
+    want = cref.msm(pts, sc, n, nthreads=cref.ncores())
+    for table in (False, True):
+        if table:
+            srs.precompute()
+        for rounds in (0, 1, 2, 3, 4):
+            pair_rounds(rounds)
+            assert zk.MultiExp(srs, sc) == want, (table, rounds)
+        pair_rounds(2)
+        lib.b200zk_msm_set_host_chunks(ctx.handle, 3)   # host-scalar chunks resume from the buckets of the chunk before
+        assert zk.MultiExp(srs, sc) == want, (table, "chunks")
+        lib.b200zk_msm_set_host_chunks(ctx.handle, 0)
+    srs.close()
+
+
+def test_pair_rounds_full_size_2_24(ctx, pair_rounds):
+    """2^24 points (the bench configuration): pair rounds off / automatic / forced agree byte for byte, and with all
+    scalars equal the result is the closed form s*(alpha^n - 1)/(alpha - 1)*G."""
+    import torch
+
+    n = 1 << 24
+    alpha_int = o.random_fr(1, 0xB2000005)[0]
+    srs = zk.SRS.NewSRS(n, o.fr_to_mont_bytes([alpha_int]), ctx)
+    srs.precompute()
+    sc = torch.randint(0, 256, (n * 32,), dtype=torch.uint8, device="cuda")
+    sc.view(n, 32)[:, 31] &= 0x1F
+    torch.cuda.synchronize()
+    got = {}
+    for rounds in (0, -1, 1, 3, 4):
+        pair_rounds(rounds)
+        res = zk.MultiExp(srs, sc, n=n)
+        ctx.sync()
+        got[rounds] = bytes(res.cpu().numpy())
+    assert len(set(got.values())) == 1, {k: v.hex()[:16] for k, v in got.items()}
+    s = o.random_fr(1, 99)[0]
+    one = np.frombuffer(o.fr_to_mont_bytes([s]), dtype=np.uint8)
+    sc.view(n, 32)[:] = torch.from_numpy(one.copy()).cuda()
+    torch.cuda.synchronize()
+    geo = (pow(alpha_int, n, o.R_MOD) - 1) * pow(alpha_int - 1, -1, o.R_MOD) % o.R_MOD
+    want = o.g1_to_bytes([o.g1_mul(o.G1_GEN, s * geo % o.R_MOD)])
+    pair_rounds(3)
+    res = zk.MultiExp(srs, sc, n=n)
+    ctx.sync()
+    assert bytes(res.cpu().numpy()) == want
+    srs.close()
