@@ -245,7 +245,8 @@ int b200zk_plonk_prove_hex(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const char* val
  * Integer-pipe microbenchmarks used as roofline denominators (synchronous).  which = 0: IMAD.WIDE.U32 multiply-
  * accumulates per second; 1: fp Montgomery multiplications per second; 2: fr Montgomery multiplications per second;
  * 3: FP64 DFMA per second; 4: IMAD.WIDE while DFMA issues beside it; 5 / 6: fp multiplications per second in the
- * schoolbook CIOS form / with the Karatsuba product (whichever the library was built with is also what 1 and 2 run). */
+ * schoolbook CIOS form / with the Karatsuba product (whichever the library was built with is also what 1 and 2 run);
+ * 7: fp products per second through the two-product sweep (a*b + c*d under one reduction; self-checked in the kernel). */
 int b200zk_microbench(b200zk_ctx* ctx, int which, double* out_ops_per_s);
 /* Per-phase device timing with CUDA events on the context stream.  Phases: 0 msm digits+histogram, 1 msm scan,
  * 2 msm scatter, 3 msm bucket accumulation, 4 msm long-run path, 5 msm bucket reduction, 6 msm final, 7 ntt pass.

@@ -3,7 +3,8 @@
 // Replaces (device side) gnark-crypto v0.9.1 ecc/bn254/g1.go: G1Affine (64 B, X||Y Montgomery limbs, (0,0) = infinity)
 // and the extended-Jacobian bucket type g1JacExtended (X, Y, ZZ, ZZZ with x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2) that
 // MultiExp accumulates into (reached from /root/reference/gnark_backend_ffi/backend/plonk/plonk.go:21,67 through
-// kzg.Commit).  Formulas: EFD "xyzz" madd-2008-s / add-2008-s / dbl-2008-s-1 with a = 0.
+// kzg.Commit).  Formulas: EFD "xyzz" madd-2008-s / add-2008-s / dbl-2008-s-1 with a = 0; Y3 = R*(Q - X3) - Y1*PPP is
+// formed as ONE two-product Montgomery sweep (fe_mul2add): 72 multiply-adds fewer per addition (1216 instead of 1288).
 #pragma once
 #include "field.cuh"
 
@@ -74,7 +75,7 @@ static __device__ __noinline__ G1XYZZ g1_double_mixed(G1Affine a) {
   Fp XX = fe_sqr(a.x);
   Fp M = fe_add(fe_dbl(XX), XX);
   Fp X3 = fe_sub(fe_sqr(M), fe_dbl(S));
-  Fp Y3 = fe_sub(fe_mul(M, fe_sub(S, X3)), fe_mul(W, a.y));
+  Fp Y3 = fe_mul2add(M, fe_sub(S, X3), W, fe_neg(a.y));
   p.x = X3;
   p.y = Y3;
   p.zz = V;
@@ -91,7 +92,7 @@ static __device__ __noinline__ G1XYZZ g1_double_v(G1XYZZ p) {
   Fp XX = fe_sqr(p.x);
   Fp M = fe_add(fe_dbl(XX), XX);
   Fp X3 = fe_sub(fe_sqr(M), fe_dbl(S));
-  Fp Y3 = fe_sub(fe_mul(M, fe_sub(S, X3)), fe_mul(W, p.y));
+  Fp Y3 = fe_mul2add(M, fe_sub(S, X3), W, fe_neg(p.y));
   p.x = X3;
   p.y = Y3;
   p.zz = fe_mul(V, p.zz);
@@ -124,7 +125,7 @@ __device__ __forceinline__ void g1_add_mixed(G1XYZZ& p, const G1Affine& a) {
   Fp PPP = fe_mul(P, PP);
   Fp Q = fe_mul(p.x, PP);
   Fp X3 = fe_sub(fe_sub(fe_sqr(R), PPP), fe_dbl(Q));
-  Fp Y3 = fe_sub(fe_mul(R, fe_sub(Q, X3)), fe_mul(p.y, PPP));
+  Fp Y3 = fe_mul2add(R, fe_sub(Q, X3), fe_neg(p.y), PPP);   // one reduction for the two products
   p.x = X3;
   p.y = Y3;
   p.zz = fe_mul(p.zz, PP);
@@ -149,7 +150,7 @@ static __device__ __noinline__ G1XYZZ g1_add_v(G1XYZZ p, G1XYZZ q) {
   Fp PPP = fe_mul(P, PP);
   Fp Q = fe_mul(U1, PP);
   Fp X3 = fe_sub(fe_sub(fe_sqr(R), PPP), fe_dbl(Q));
-  Fp Y3 = fe_sub(fe_mul(R, fe_sub(Q, X3)), fe_mul(S1, PPP));
+  Fp Y3 = fe_mul2add(R, fe_sub(Q, X3), fe_neg(S1), PPP);
   p.x = X3;
   p.y = Y3;
   p.zz = fe_mul(fe_mul(p.zz, q.zz), PP);

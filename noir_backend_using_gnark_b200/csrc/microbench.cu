@@ -6,6 +6,8 @@
 //   which = 3: FP64 DFMA per second (8 independent chains per thread) -- the other multiplier array of the SM
 //   which = 4: IMAD.WIDE.U32 per second while the same threads also issue DFMA (1:1), to see whether the pipes overlap
 //   which = 5 / 6: fp multiplications per second in the schoolbook CIOS form / with the Karatsuba product (field.cuh)
+//   which = 7: fp PRODUCTS per second through the two-product sweep fe_mul2add (a*b + c*d with one reduction); every
+//              thread first checks it against fe_add(fe_mul, fe_mul) on its operands and the kernel traps on a mismatch
 #include "common.cuh"
 #include "field.cuh"
 
@@ -109,6 +111,28 @@ __global__ void __launch_bounds__(256) mb_mul_form_kernel(uint4* out, unsigned s
 }
 
 template <class P>
+__global__ void __launch_bounds__(256) mb_mul2add_kernel(uint4* out, unsigned seed) {
+  Fe<P> x = fe_one<P>(), y = fe_one<P>(), m = fe_one<P>(), k = fe_one<P>();
+  x.l[0] ^= seed + threadIdx.x;
+  y.l[1] ^= seed + blockIdx.x + 7u * threadIdx.x;
+  m.l[2] ^= seed + 3u * threadIdx.x;
+  k.l[3] ^= seed + 5u * threadIdx.x;
+  {
+    // extreme operands too: modulus - 1 - (small)
+    Fe<P> big = fe_neg(x), big2 = fe_neg(m);
+    if (!fe_eq(fe_mul2add(x, m, y, k), fe_add(fe_mul(x, m), fe_mul(y, k))) ||
+        !fe_eq(fe_mul2add(big, big2, big, big), fe_add(fe_mul(big, big2), fe_mul(big, big))))
+      __trap();
+  }
+  for (int it = 0; it < MB_ITERS; it++) {
+    x = fe_mul2add(x, m, y, k);
+    y = fe_mul2add(y, k, x, m);
+  }
+  Fe<P> s = fe_add(x, y);
+  if (s.l[0] == 0x12345678u && s.l[7] == 0x9abcdef0u) fe_store(out, s);
+}
+
+template <class P>
 __global__ void __launch_bounds__(256) mb_mul_kernel(uint4* out, unsigned seed) {
   Fe<P> x = fe_one<P>(), y = fe_one<P>(), m = fe_one<P>();
   // every operand depends on the lane: warp-uniform chains would be moved to the uniform datapath (UIMAD) and
@@ -125,7 +149,7 @@ __global__ void __launch_bounds__(256) mb_mul_kernel(uint4* out, unsigned seed) 
 }
 
 int microbench_run(b200zk_ctx* ctx, int which, double* out_ops_per_s) {
-  if (!out_ops_per_s || which < 0 || which > 6) return B200ZK_ERR_BAD_ARG;
+  if (!out_ops_per_s || which < 0 || which > 7) return B200ZK_ERR_BAD_ARG;
   void* sink = nullptr;
   B200ZK_CUDA(ctx, cudaMalloc(&sink, 64));
   cudaEvent_t e0, e1;
@@ -140,6 +164,7 @@ int microbench_run(b200zk_ctx* ctx, int which, double* out_ops_per_s) {
     else if (which == 2) mb_mul_kernel<FrParams><<<blocks, threads, 0, ctx->stream>>>((uint4*)sink, 17u + rep);
     else if (which == 5) mb_mul_form_kernel<FpParams, 0><<<blocks, threads, 0, ctx->stream>>>((uint4*)sink, 17u + rep);
     else if (which == 6) mb_mul_form_kernel<FpParams, 1><<<blocks, threads, 0, ctx->stream>>>((uint4*)sink, 17u + rep);
+    else if (which == 7) mb_mul2add_kernel<FpParams><<<blocks, threads, 0, ctx->stream>>>((uint4*)sink, 17u + rep);
     else if (which == 3) mb_dfma_kernel<<<blocks, threads, 0, ctx->stream>>>((double*)sink, 17u + rep);
     else mb_mixed_kernel<<<blocks, threads, 0, ctx->stream>>>((unsigned long long*)sink, 17u + rep);
     B200ZK_LAUNCH_CHECK(ctx, "microbench kernel");
@@ -150,6 +175,7 @@ int microbench_run(b200zk_ctx* ctx, int which, double* out_ops_per_s) {
     double per_thread = MB_ITERS * 2.0;                  // which = 1, 2: two multiplication chains
     if (which == 0) per_thread = (MB_ITERS / 2) * 64.0;  // 4 iterations x 4 chains x 4 IMAD.WIDE
     if (which == 3) per_thread = MB_ITERS * 32.0;
+    if (which == 7) per_thread = MB_ITERS * 4.0;         // two sweeps of two products each
     if (which == 4) per_thread = (MB_ITERS / 2) * 32.0;  // IMAD.WIDE only (4 x 8); the DFMA count is twice that
     double ops = (double)blocks * threads * per_thread;
     double rate = ops / (ms * 1e-3);

@@ -1,4 +1,4 @@
-"""python scripts/fieldmul_probe.py: field-multiplier microbenchmarks (b200zk_microbench 0..6), the 2^24 MSM phases and
+"""python scripts/fieldmul_probe.py: field-multiplier microbenchmarks (b200zk_microbench 0..7), the 2^24 MSM phases and
 the 2^24 NTT with the library as built — run once per build variant to fill profiles/r02_fieldmul.md."""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -7,8 +7,9 @@ import noir_backend_using_gnark_b200 as zk
 from noir_backend_using_gnark_b200 import plonk as zkp
 from sweep import images
 ctx = zk.Context(0)
-names = ["imad_wide", "fp_mul(lib)", "fr_mul(lib)", "dfma", "imad_wide_beside_dfma", "fp_mul_schoolbook", "fp_mul_karatsuba"]
-print({names[k]: round(ctx.microbench(k) / 1e9, 2) for k in range(7)}, "G/s")
+names = ["imad_wide", "fp_mul(lib)", "fr_mul(lib)", "dfma", "imad_wide_beside_dfma", "fp_mul_schoolbook", "fp_mul_karatsuba",
+         "fp_products_in_mul2add"]
+print({names[k]: round(ctx.microbench(k) / 1e9, 2) for k in range(8)}, "G/s")
 ext = ctx.torch_stream()
 lg = int(sys.argv[1]) if len(sys.argv) > 1 else 24
 n = 1 << lg
