@@ -759,9 +759,11 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
     acc_ms, acc_cnt = phases["msm_accumulate"]
     acc_ms_per = acc_ms / max(acc_cnt, 1)
     algorithmic = MACS_PER_POINT * n / (acc_ms_per * 1e-3) if acc_ms_per > 0 else 0.0
-    # MACs the kernel really issues: one mixed XYZZ addition = 8 multiplications (136 MACs) + 2 squarings (100 MACs);
+    # MACs the kernel really issues: one mixed XYZZ addition = 6 multiplications (136 MACs) + 2 squarings (100 MACs) + one
+    # two-product sweep for Y3 (fe_mul2add: 200 MACs instead of 2 x 136) = 1216;
     # additions per point = number of windows (12 with the 2^24 window table, 16 classic windows)
-    executed = (srs_windows * (8 * 136 + 2 * 100) * n / (acc_ms_per * 1e-3)) if (srs_windows and acc_ms_per > 0) else None
+    MACS_PER_ADD = 6 * 136 + 2 * 100 + 200
+    executed = (srs_windows * MACS_PER_ADD * n / (acc_ms_per * 1e-3)) if (srs_windows and acc_ms_per > 0) else None
     phase_share = {k: round(v[0] / max(ms_total, 1e-9), 4) for k, v in phases.items() if v[1]}
 
     ntt_info = None
@@ -850,8 +852,8 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
         "roofline": {"bound": "int-mad (fma-pipe IMAD.WIDE; MSM is not HBM- or tensor-bound)", "kernel": "msm_accumulate_kernel",
                      "achieved": (executed / 1e12) if executed else None, "peak": imad_peak / 1e12, "unit": "TMAC/s",
                      "frac": (executed / imad_peak) if (executed and imad_peak) else None,
-                     "note": "achieved = 32x32 multiply-accumulates the kernel executes (windows x (8 mul x 136 + 2 sqr x 100) per "
-                             "point) / CUDA-event time of the kernel; frac_algorithmic uses SURVEY 8d's unit (16 windows x 10 modmul "
+                     "note": "achieved = 32x32 multiply-accumulates the kernel executes (windows x (6 mul x 136 + 2 sqr x 100 + one "
+                             "two-product sweep of 200) per point) / CUDA-event time of the kernel; frac_algorithmic uses SURVEY 8d's unit (16 windows x 10 modmul "
                              "x 136 = 21760 MACs per point) and exceeds the executed figure because the window table needs fewer "
                              "additions per point",
                      "achieved_algorithmic": algorithmic / 1e12,

@@ -295,10 +295,9 @@ __global__ void __launch_bounds__(256) k_quotient(QuotientArgs q) {
   const Fr L = fe_load_ro<FrParams>(q.el + 2 * i), R = fe_load_ro<FrParams>(q.er + 2 * i),
            O = fe_load_ro<FrParams>(q.eo + 2 * i);
   // gate: ql*l + qr*r + qm*l*r + qo*o + qk
-  Fr ic = fe_mul(fe_load_ro<FrParams>(q.ql + 2 * i), L);
-  ic = fe_add(ic, fe_mul(fe_load_ro<FrParams>(q.qr + 2 * i), R));
-  ic = fe_add(ic, fe_mul(fe_mul(fe_load_ro<FrParams>(q.qm + 2 * i), L), R));
-  ic = fe_add(ic, fe_mul(fe_load_ro<FrParams>(q.qo + 2 * i), O));
+  // (pairs of products share one Montgomery reduction: fe_mul2add)
+  Fr ic = fe_mul2add(fe_load_ro<FrParams>(q.ql + 2 * i), L, fe_load_ro<FrParams>(q.qr + 2 * i), R);
+  ic = fe_add(ic, fe_mul2add(fe_mul(fe_load_ro<FrParams>(q.qm + 2 * i), L), R, fe_load_ro<FrParams>(q.qo + 2 * i), O));
   ic = fe_add(ic, fe_load_ro<FrParams>(q.eqk + 2 * i));
   // permutation: zs * prod(w + beta*s + gamma) - z * prod(w + beta*u^k*x + gamma),  x = u * w_{4n}^nat
   const Fr x = fe_mul(coset_u(), omega_pow(q.tw_big, nat, N >> 1));
@@ -307,12 +306,10 @@ __global__ void __launch_bounds__(256) k_quotient(QuotientArgs q) {
   Fr a = fe_add(Lg, fe_mul(beta, x));
   a = fe_mul(a, fe_add(Rg, fe_mul(arg(q.beta_u), x)));
   a = fe_mul(a, fe_add(Og, fe_mul(arg(q.beta_uu), x)));
-  a = fe_mul(a, z);
   Fr b = fe_add(Lg, fe_mul(beta, fe_load_ro<FrParams>(q.s1 + 2 * i)));
   b = fe_mul(b, fe_add(Rg, fe_mul(beta, fe_load_ro<FrParams>(q.s2 + 2 * i))));
   b = fe_mul(b, fe_add(Og, fe_mul(beta, fe_load_ro<FrParams>(q.s3 + 2 * i))));
-  b = fe_mul(b, fe_load_ro<FrParams>(ez_s + 2 * ishift));
-  const Fr perm = fe_sub(b, a);
+  const Fr perm = fe_mul2add(b, fe_load_ro<FrParams>(ez_s + 2 * ishift), a, fe_neg(z));   // b * zs - a * z
   // (z - 1) * L1
   const Fr one_term = fe_mul(fe_sub(z, fe_one<FrParams>()), fe_load_ro<FrParams>(q.lone + 2 * i));
   Fr c = fe_add(fe_mul(one_term, alpha), perm);
