@@ -55,6 +55,16 @@ if "msm" in parts:
     lib.b200zk_msm_set_host_chunks(ctx.handle, 3)
     assert zk.MultiExp(srs, sc) == r0              # chunked host path (copy stream + partial sums)
     lib.b200zk_msm_set_host_chunks(ctx.handle, 0)
+    for rounds in (1, 3):                          # batched-affine pair rounds: padded runs, pair kernels, shifted run bounds
+        lib.b200zk_msm_set_pair_rounds(ctx.handle, rounds)
+        lib.b200zk_msm_set_small_path(ctx.handle, 0)
+        assert zk.MultiExp(srs, sc) == r0
+        assert zk.MultiExp(srs, same) == r1
+        lib.b200zk_msm_set_window(ctx.handle, 9)   # classic windows
+        assert zk.MultiExp(srs, sc) == r0
+        lib.b200zk_msm_set_window(ctx.handle, 0)
+    lib.b200zk_msm_set_pair_rounds(ctx.handle, -1)
+    lib.b200zk_msm_set_small_path(ctx.handle, 1)
     comp = srs.download_compressed(0, 64)
     zk.SRS.FromCompressed(comp, ctx).close()
     srs.close()
