@@ -592,3 +592,12 @@ def test_pair_rounds_full_size_2_24(ctx, pair_rounds):
     ctx.sync()
     assert bytes(res.cpu().numpy()) == want
     srs.close()
+
+
+def test_two_product_sweep_self_check(ctx):
+    """b200zk_microbench(ctx, 7): every thread compares fe_mul2add(a, b, c, d) with fe_add(fe_mul(a, b), fe_mul(c, d)) on
+    lane-dependent and on near-modulus operands and traps on a mismatch (a trap surfaces as a CUDA error here); the rate it
+    returns must beat the plain product's (one reduction for two products)."""
+    two = ctx.microbench(7)
+    one = ctx.microbench(5)
+    assert two > 1.15 * one, (two, one)
