@@ -89,6 +89,24 @@ class Context:
 
         return torch.cuda.ExternalStream(self.stream_ptr, device=self.device)
 
+    def after_torch(self) -> None:
+        """Device-tensor entry points: the library works on its own non-blocking stream, so the work already queued on
+        torch's current stream (the producers of the tensors passed in) is ordered before it here.  Results are ready
+        after `sync()`, or for torch after `before_torch()`."""
+        import torch
+
+        cur = torch.cuda.current_stream(self.device)
+        if cur.cuda_stream != self.stream_ptr:
+            self.torch_stream().wait_stream(cur)
+
+    def before_torch(self) -> None:
+        """torch's current stream waits for everything enqueued on the library's stream so far"""
+        import torch
+
+        cur = torch.cuda.current_stream(self.device)
+        if cur.cuda_stream != self.stream_ptr:
+            cur.wait_stream(self.torch_stream())
+
 
 _default: dict[int, Context] = {}
 
@@ -124,6 +142,7 @@ class Domain:
         if hasattr(a, "is_cuda") and a.is_cuda:
             assert a.is_contiguous() and a.numel() * a.element_size() == self.Cardinality * 32
             assert a.device.index == self.ctx.device
+            self.ctx.after_torch()
             rc = lib.b200zk_ntt_dev(h, a.data_ptr(), self.log2n, inverse, decimation, int(bool(coset)))
             _lib.check(h, rc)
             return a
@@ -151,6 +170,7 @@ def BitReverse(a, ctx: Optional[Context] = None):
         n = a.numel() * a.element_size() // 32
         log2n = _log2_ceil(n)
         assert 1 << log2n == n
+        ctx.after_torch()
         _lib.check(h, lib.b200zk_bit_reverse_dev(h, a.data_ptr(), log2n))
         return a
     if isinstance(a, bytes):
@@ -269,6 +289,7 @@ def MultiExp(srs: SRS, scalars, n: Optional[int] = None, first_base: int = 0, ou
             n = scalars.numel() * scalars.element_size() // 32
         if out is None:
             out = torch.empty(128 if partial else 64, dtype=torch.uint8, device=scalars.device)
+        ctx.after_torch()
         rc = lib.b200zk_msm_g1_dev(h, srs.handle, first_base, scalars.data_ptr(), n, out.data_ptr(), int(partial))
         _lib.check(h, rc)
         return out

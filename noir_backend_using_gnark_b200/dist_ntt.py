@@ -129,7 +129,7 @@ class DistributedDomain:
         class _View:  # zero-copy torch view of the library-owned exchange buffer
             __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (own.value, False), "version": 2}
 
-        self._exchange = torch.as_tensor(_View(), device="cuda:%d" % self.ctx.device)
+        self._exchange_buf = torch.as_tensor(_View(), device="cuda:%d" % self.ctx.device)
         self._flag = torch.zeros(1, dtype=torch.int32, device="cuda:%d" % self.ctx.device)
 
     def _stream_barrier(self) -> None:
@@ -147,7 +147,7 @@ class DistributedDomain:
                                                lay.log2c, inverse, decimation, coset)
         _lib.check(h, rc)
         self._stream_barrier()   # all peers' stores have landed
-        ex = self._exchange
+        ex = self._exchange_buf
         if decimation == DIF:
             self._device_half(ex, x, 1, inverse, decimation, coset)   # reads Z from the exchange buffer, writes Y
             return x
