@@ -151,6 +151,11 @@ int b200zk_msm_set_reduce_chunk(b200zk_ctx* ctx, int chunk_log);
 /* tests: with a window table, MSMs of up to 2^17 (point, window) terms skip the bucket pipeline (one thread per term,
  * two launches: the sizes of the reference's own test circuits); 0 forces the bucket pipeline there too, 1 = default */
 int b200zk_msm_set_small_path(b200zk_ctx* ctx, int on);
+/* The counting sort's scatter places the (point, window) entries in bucket-range passes so that the partially written
+ * sectors of one pass stay in L2 until they are complete (random 4-byte stores into an array far larger than L2 otherwise
+ * become 32-byte read-modify-writes in DRAM): 0 = number of passes from the bucket count (default; 7 at 2^21 buckets),
+ * 1 = single pass, k <= 256 = forced (tests / tuning).  The result does not depend on it. */
+int b200zk_msm_set_scatter_passes(b200zk_ctx* ctx, int passes);
 /* Batched-affine pair rounds of the bucket accumulation: the counting sort pads every bucket's run to a multiple of
  * 2^rounds entries and `rounds` passes of out[o] = in[2o] + in[2o+1] (affine additions, one inversion per lane per
  * batch: 5M + 1S per addition instead of 8M + 2S) pre-sum the runs before the extended-Jacobian walk.

@@ -86,6 +86,7 @@ def load() -> C.CDLL:
         "b200zk_msm_set_host_chunks": (i, [vp, i]),
         "b200zk_msm_set_small_path": (i, [vp, i]),
         "b200zk_msm_set_pair_rounds": (i, [vp, i]),
+        "b200zk_msm_set_scatter_passes": (i, [vp, i]),
         "b200zk_msm_set_reduce_chunk": (i, [vp, i]),
         "b200zk_msm_g1_dev": (i, [vp, vp, sz, vp, sz, vp, i]),
         "b200zk_g1_sum_dev": (i, [vp, vp, sz, vp]),

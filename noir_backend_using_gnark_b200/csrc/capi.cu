@@ -78,6 +78,10 @@ int b200zk_init(int device, b200zk_ctx** out) {
     const int r = atoi(pr);
     if (r >= -1 && r <= 6) ctx->msm_pair_rounds = r;
   }
+  if (const char* sm = getenv("B200ZK_MSM_SCATTER_PASSES")) {
+    const int v = atoi(sm);
+    if (v >= 0 && v <= 256) ctx->msm_scatter_passes = v;
+  }
   if (const char* pk = getenv("B200ZK_MSM_PAIR_KMAX")) {
     const int k = atoi(pk);
     if (k >= 0 && k <= 4096) ctx->msm_pair_kmax = k;
@@ -95,7 +99,7 @@ void b200zk_destroy(b200zk_ctx* ctx) {
   for (int l = 0; l < MSM_LANES; l++) {
     MsmWorkspace& w = ctx->ws[l];
     DeviceBuf* bufs[] = {&w.msm_digits, &w.msm_sorted, &w.msm_counts, &w.msm_starts, &w.msm_cursor, &w.msm_buckets,
-                         &w.msm_tmp, &w.msm_small, &w.msm_scan_tmp, &w.msm_big, &w.msm_pairs};
+                         &w.msm_tmp, &w.msm_small, &w.msm_scan_tmp, &w.msm_big, &w.msm_pairs, &w.msm_keys};
     for (auto bp : bufs) free_buf(*bp);
     if (l > 0 && w.stream) cudaStreamDestroy(w.stream);
     if (w.done) cudaEventDestroy(w.done);
@@ -398,6 +402,12 @@ int b200zk_plonk_set_commit_lanes(b200zk_ctx* ctx, int lanes) {
 int b200zk_msm_set_reduce_chunk(b200zk_ctx* ctx, int chunk_log) {
   if (!ctx || (chunk_log != 0 && chunk_log != 3 && chunk_log != 4 && chunk_log != 5)) return B200ZK_ERR_BAD_ARG;
   ctx->msm_chunk_log = chunk_log;
+  return B200ZK_OK;
+}
+
+int b200zk_msm_set_scatter_passes(b200zk_ctx* ctx, int passes) {
+  if (!ctx || passes < 0 || passes > 256) return B200ZK_ERR_BAD_ARG;
+  ctx->msm_scatter_passes = passes;
   return B200ZK_OK;
 }
 

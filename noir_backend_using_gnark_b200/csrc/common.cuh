@@ -47,7 +47,7 @@ namespace b200zk {
 static constexpr int MSM_LANES = 3;
 struct MsmWorkspace {
   DeviceBuf msm_digits, msm_sorted, msm_counts, msm_starts, msm_cursor, msm_buckets, msm_tmp, msm_small, msm_scan_tmp,
-      msm_big, msm_pairs;
+      msm_big, msm_pairs, msm_keys;
   cudaStream_t stream = nullptr;   // lane 0: the context stream
   cudaEvent_t done = nullptr;      // recorded after the lane's last MSM (lanes > 0)
 };
@@ -82,6 +82,7 @@ struct b200zk_ctx {
   int msm_no_tiny = 0;           // tests: force the bucket pipeline also for small table-mode MSMs
   int msm_pair_rounds = -1;      // batched-affine pair rounds before the bucket walk: -1 = from the size, 0 = off, r = forced
   int msm_pair_kmax = 0;         // tuning: additions per inversion per lane (0 = default)
+  int msm_scatter_passes = 0;    // tests / tuning: bucket-range passes of the counting sort's scatter (0 = from the bucket count)
   uint64_t launches = 0;
   char cuda_err[256] = {0};
   int forced_window = 0;

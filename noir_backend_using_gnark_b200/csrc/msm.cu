@@ -38,6 +38,13 @@ static constexpr size_t SMALL_TABLE_N = 2048;     // head of a large base set th
 static constexpr int MAX_WINDOWS = 64;
 static constexpr int SLICE = 1024;             // chunk results per CTA in the bit-plane sums
 static constexpr int MAX_PLANES = 24;
+static constexpr unsigned NO_KEY = 0x7fffffffu;                   // record of a zero digit in the scatter passes' key stream
+// scatter passes: a pass should leave no more partially written 32-byte sectors open (one per bucket) than L2 keeps until
+// they are complete.  Measured at 2^24 points, 2^21 buckets: 1 pass 5.75 ms, 5 passes 3.29, 7 passes 3.08, 9 passes 3.36,
+// 13 passes 3.96, 17 passes 4.65 (every pass streams all records once more); 2^19 buckets: 2 passes 0.69 against 0.73 ms.
+static constexpr size_t SCATTER_OPEN_BYTES = (size_t)10 << 20;
+static constexpr unsigned SCATTER_MAX_PASSES = 16;
+static constexpr size_t SCATTER_PASS_MIN_ENTRIES = (size_t)1 << 24;   // below: the scatter is a small part of a small MSM
 
 struct MsmShape {
   unsigned c;           // window bits (the widest window in table mode)
@@ -98,7 +105,7 @@ __device__ __forceinline__ Fr load_scalar_regular(const uint4* __restrict__ scal
 // 1. histogram, 3. scatter
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) msm_hist_kernel(const uint4* __restrict__ scalars, size_t n, MsmShape sh,
-                                                       unsigned* __restrict__ counts) {
+                                                       unsigned* __restrict__ counts, unsigned* __restrict__ keys_out) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   const unsigned active = __ballot_sync(0xffffffffu, i < n);
   if (i >= n) return;
@@ -107,6 +114,8 @@ __global__ void __launch_bounds__(256) msm_hist_kernel(const uint4* __restrict__
   for_each_digit(s, sh, [&](unsigned w, int d) {
     const unsigned mag = d < 0 ? (unsigned)(-d) : (unsigned)d;
     const unsigned key = w * sh.key_stride + (mag - 1);
+    // window-major (bucket | sign) record for the scatter passes; NO_KEY for a zero digit
+    if (keys_out) keys_out[(size_t)w * n + i] = d == 0 ? NO_KEY : (key | (d < 0 ? 0x80000000u : 0u));
     if (w + 1 == sh.W) {
       // the top window holds only 254 - c*(W-1) scalar bits: few distinct buckets, so the lanes of a warp collide
       // on the same counters -> aggregate per warp (one atomic per distinct bucket)
@@ -172,6 +181,44 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint4* __restric
 #pragma unroll
   for (int w = 0; w < MAXW; w++)
     if (pos[w] != 0xffffffffu) sorted[pos[w]] = entry[w];
+}
+
+// Large sorts.  What bounds the scatter above is not its atomics but the 4-byte stores at random positions of an array
+// far larger than L2: each becomes a 32-byte read-modify-write in DRAM (11.4 GB moved for 0.8 GB of entries at 2^24; with
+// the stores confined to an L2-resident window the same kernel takes 2.2 instead of 5.75 ms).  So the entries are placed
+// in gridDim.y PASSES: pass p takes only bucket range p, whose slice of the sorted array (contiguous, the buckets being
+// laid out in order) stays in L2 until it is complete and is written back once.  A pass does not repeat the digit
+// recoding: it streams the (bucket | sign) records msm_hist_kernel parked window-major (4 B per entry, coalesced).
+template <int MAXW>
+__global__ void __launch_bounds__(256) msm_scatter_pass_kernel(const unsigned* __restrict__ keys, size_t n, MsmShape sh,
+                                                               unsigned keys_per_pass, unsigned* __restrict__ cursor,
+                                                               unsigned* __restrict__ sorted) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const unsigned active = __ballot_sync(0xffffffffu, i < n);
+  if (i >= n) return;
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned key_lo = blockIdx.y * keys_per_pass;
+  unsigned recs[MAXW];   // all of the point's records in flight at once (streamed: they must not push the slice out of L2)
+#pragma unroll
+  for (int w = 0; w < MAXW; w++) recs[w] = (unsigned)w < sh.W ? __ldcs(keys + (size_t)w * n + i) : NO_KEY;
+#pragma unroll
+  for (int w = 0; w < MAXW; w++) {
+    if ((unsigned)w >= sh.W) break;
+    const unsigned rec = recs[w];
+    const unsigned key = rec & 0x7fffffffu;
+    const bool hit = key - key_lo < keys_per_pass;             // NO_KEY is above every range
+    unsigned pos = 0;
+    if (w + 1 == sh.W && sh.tab_stride == 0) {
+      // classic mode: the narrow top window has a handful of buckets -> one cursor bump per distinct bucket of the warp
+      const unsigned grp = __match_any_sync(active, hit ? key : 0xffffffffu);
+      const unsigned leader = (unsigned)(__ffs(grp) - 1);
+      if (hit && lane == leader) pos = atomicAdd(&cursor[key], (unsigned)__popc(grp));
+      pos = __shfl_sync(grp, pos, leader) + __popc(grp & ((1u << lane) - 1u));
+    } else if (hit) {
+      pos = atomicAdd(&cursor[key], 1u);
+    }
+    if (hit) sorted[pos] = (w * sh.tab_stride + sh.first + (unsigned)i) | (rec & 0x80000000u);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -921,6 +968,22 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
   const unsigned big_cap = nbuckets / 4 + 16;
   const size_t max_big_chunks = total / BIG_CHUNK + big_cap + 1;
 
+  // scatter passes (ctx->msm_scatter_passes: 0 = from the bucket count, 1 = single pass, k = forced)
+  unsigned passes = 1;
+  if (ctx->msm_scatter_passes > 0) {
+    passes = (unsigned)ctx->msm_scatter_passes;
+  } else if (total >= SCATTER_PASS_MIN_ENTRIES) {
+    const size_t want = ((size_t)nbuckets * 32 + SCATTER_OPEN_BYTES - 1) / SCATTER_OPEN_BYTES;
+    passes = (unsigned)(want > SCATTER_MAX_PASSES ? SCATTER_MAX_PASSES : want);
+  }
+  if (passes > nbuckets) passes = nbuckets;
+  if (passes < 1) passes = 1;
+  const unsigned keys_per_pass = (nbuckets + passes - 1) / passes;
+  unsigned* keys = nullptr;
+  if (passes > 1) {
+    B200ZK_TRY(ensure(ctx, ws.msm_keys, total * sizeof(unsigned), st));
+    keys = (unsigned*)ws.msm_keys.p;
+  }
   B200ZK_TRY(ensure(ctx, ws.msm_sorted, total_bound * sizeof(unsigned), st));
   if (R) B200ZK_TRY(ensure(ctx, ws.msm_pairs, ((total_bound >> 1) + (R > 1 ? (total_bound >> 2) : 0) + 2) * 64, st));
   B200ZK_TRY(ensure(ctx, ws.msm_counts, (size_t)(nbuckets + 1) * 4, st));
@@ -964,7 +1027,7 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
   {
     PhaseTimer pt(ctx, PH_MSM_DIGITS, st);
     unsigned blocks = (unsigned)((n + 255) / 256);
-    msm_hist_kernel<<<blocks, 256, 0, st>>>((const uint4*)scalars_dev, n, sh, counts);
+    msm_hist_kernel<<<blocks, 256, 0, st>>>((const uint4*)scalars_dev, n, sh, counts, keys);
     B200ZK_LAUNCH_CHECK(ctx, "msm_hist_kernel");
   }
   {
@@ -990,7 +1053,14 @@ int msm_run(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_base, const
   {
     PhaseTimer pt(ctx, PH_MSM_SCATTER, st);
     unsigned blocks = (unsigned)((n + 255) / 256);
-    if (sh.W <= 13)
+    if (keys) {   // x fastest: all CTAs of pass p are placed before those of pass p + 1
+      if (sh.W <= 13)
+        msm_scatter_pass_kernel<13><<<dim3(blocks, passes), 256, 0, st>>>(keys, n, sh, keys_per_pass, cursor, sorted);
+      else if (sh.W <= 20)
+        msm_scatter_pass_kernel<20><<<dim3(blocks, passes), 256, 0, st>>>(keys, n, sh, keys_per_pass, cursor, sorted);
+      else
+        msm_scatter_pass_kernel<MAX_WINDOWS><<<dim3(blocks, passes), 256, 0, st>>>(keys, n, sh, keys_per_pass, cursor, sorted);
+    } else if (sh.W <= 13)
       msm_scatter_kernel<13><<<blocks, 256, 0, st>>>((const uint4*)scalars_dev, n, sh, cursor, sorted);
     else if (sh.W <= 20)
       msm_scatter_kernel<20><<<blocks, 256, 0, st>>>((const uint4*)scalars_dev, n, sh, cursor, sorted);

@@ -36,6 +36,7 @@ def test_strerror_and_null_handling(lib_built):
     assert lib.b200zk_msm_set_small_path(None, 1) == -3
     assert lib.b200zk_msm_set_host_chunks(None, 2) == -3
     assert lib.b200zk_msm_set_pair_rounds(None, 2) == -3
+    assert lib.b200zk_msm_set_scatter_passes(None, 2) == -3
     assert b"constraint" in lib.b200zk_strerror(-6)
 
 

@@ -601,3 +601,57 @@ def test_two_product_sweep_self_check(ctx):
     two = ctx.microbench(7)
     one = ctx.microbench(5)
     assert two > 1.15 * one, (two, one)
+
+
+# ---- bucket-range scatter passes (b200zk_msm_set_scatter_passes) -----------------------------------------------------
+@pytest.mark.parametrize("passes", [2, 7, 64])
+def test_scatter_passes_small_and_skewed(ctx, passes):
+    """The scatter in bucket-range passes (key records parked by the histogram kernel) must place exactly the entries of
+    the single-pass scatter: special scalars and points, every window size (classic windows use the warp-aggregated top
+    window), the window table, all-equal scalars (one bucket per window takes everything), host-scalar chunks, and on
+    top of pair rounds."""
+    lib = zk.load()
+    try:
+        n = 3000
+        pts = structured(n).copy()
+        pts[5 * 64 : 6 * 64] = 0
+        vals = o.random_fr(n, 23)
+        vals[0] = 0
+        vals[1] = 1
+        vals[2] = o.R_MOD - 1
+        vals[7] = 1 << 15
+        sc = np.frombuffer(o.fr_to_mont_bytes(vals), dtype=np.uint8)
+        same = np.tile(sc[32 * 11 : 32 * 12], n)
+        srs = zk.SRS(pts, ctx)
+        want, want_same = cref.msm(pts, sc, n, nthreads=4), cref.msm(pts, same, n, nthreads=4)
+        lib.b200zk_msm_set_small_path(ctx.handle, 0)
+        for table in (False, True):
+            if table:
+                srs.precompute()
+            for c in (0, 6, 11, 16):
+                lib.b200zk_msm_set_window(ctx.handle, c)
+                lib.b200zk_msm_set_scatter_passes(ctx.handle, 1)
+                assert zk.MultiExp(srs, sc) == want, (table, c, "single")
+                lib.b200zk_msm_set_scatter_passes(ctx.handle, passes)
+                assert zk.MultiExp(srs, sc) == want, (table, c)
+                assert zk.MultiExp(srs, same) == want_same, (table, c, "all equal")
+            lib.b200zk_msm_set_window(ctx.handle, 0)
+            lib.b200zk_msm_set_pair_rounds(ctx.handle, 2)
+            assert zk.MultiExp(srs, sc) == want, (table, "pair rounds")
+            lib.b200zk_msm_set_pair_rounds(ctx.handle, -1)
+        srs.close()
+        n = (1 << 16) + 5
+        pts = structured(n)
+        sc = cref.random_fr(n, 0xB2000001 + 9)
+        srs = zk.SRS(pts, ctx)
+        srs.precompute()
+        want = cref.msm(pts, sc, n, nthreads=cref.ncores())
+        lib.b200zk_msm_set_host_chunks(ctx.handle, 3)
+        assert zk.MultiExp(srs, sc) == want
+        srs.close()
+    finally:
+        lib.b200zk_msm_set_scatter_passes(ctx.handle, 0)
+        lib.b200zk_msm_set_small_path(ctx.handle, 1)
+        lib.b200zk_msm_set_window(ctx.handle, 0)
+        lib.b200zk_msm_set_host_chunks(ctx.handle, 0)
+        lib.b200zk_msm_set_pair_rounds(ctx.handle, -1)
