@@ -819,8 +819,8 @@ int msm_precompute_run(b200zk_ctx* ctx, b200zk_bases* bases, int c_req) {
   // number of windows from the size (or from a requested maximum width c_req)
   unsigned W;
   if (c_req) W = (255 + (unsigned)c_req - 1) / (unsigned)c_req;
-  else if (lg >= 24) W = 12;   // widths 22,22,22,21 x9  -> 2^21 buckets
-  else if (lg >= 19) W = 13;   // widths 20 x8, 19 x5     -> 2^19 buckets (2^23 points: 19.4 ms against 20.3 ms with W = 12)
+  else if (lg >= 23) W = 12;   // widths 22,22,22,21 x9  -> 2^21 buckets (2^23 points: 19.15 ms, 19.27 ms with W = 13)
+  else if (lg >= 19) W = 13;   // widths 20 x8, 19 x5     -> 2^19 buckets
   else if (lg >= 15) W = 15;   // widths 17 x15           -> 2^16 buckets
   else if (lg >= 14) W = 16;   // widths 16 x15, 15       -> 2^15 buckets
   else if (lg >= 13) W = 17;   // widths 15 x17           -> 2^14 buckets
