@@ -142,7 +142,8 @@ int b200zk_msm_g1_dev(b200zk_ctx* ctx, const b200zk_bases* bases, size_t first_b
 /* out_affine_dev (64 B) = canonical affine of the sum of `count` extended-Jacobian partials (128 B each). */
 int b200zk_g1_sum_dev(b200zk_ctx* ctx, const void* partials_dev, size_t count, void* out_affine_dev);
 /* b200zk_msm_g1 (host scalars) splits large inputs by point range so that the host-to-device copy of one chunk runs
- * under the MSM of the previous one; 0 = choose from n (from 2^23 points: three chunks of 1/8, 3/8 and 1/2 of the points — only the first copy is exposed), 1 = never split, up to 8 equal chunks */
+ * under the MSM of the previous one; 0 = choose from n (from 2^23 points: three chunks of 1/8, 3/8 and 1/2 of the points — only the first copy is exposed;
+ * from 2^20 points: 1/4 and 3/4), 1 = never split, up to 8 equal chunks */
 int b200zk_msm_set_host_chunks(b200zk_ctx* ctx, int chunks);
 /* tests / tuning: buckets per running-sum chunk of the bucket reduction, as a power of two: 3 (short dependent chains,
  * chosen up to 2^17 buckets where the reduction is latency-bound), 4 (up to 2^19 buckets), 5 (fewer chunk results, chosen

@@ -331,9 +331,11 @@ static int msm_host_scalars(b200zk_ctx* ctx, const b200zk_bases* bases, size_t f
   *result_dev = stage;
   // Large inputs are split by point range so that the PCIe copy of chunk i+1 runs under the MSM of chunk i (the sum of
   // the partial MSMs is the MSM: the canonical affine result does not depend on the split).  Only the copy of the FIRST
-  // chunk is exposed, so the automatic split is uneven — 1/8, 3/8, 1/2 of the points: a short first copy, and every
-  // later copy still shorter than the MSM it hides under.
-  unsigned chunks = ctx->msm_host_chunks > 0 ? (unsigned)ctx->msm_host_chunks : (n >= ((size_t)1 << 23) ? 3u : 1u);
+  // chunk is exposed, so the automatic split is uneven — 1/8, 3/8, 1/2 of the points from 2^23 points (a short first
+  // copy, and every later copy still shorter than the MSM it hides under), 1/4, 3/4 from 2^20 points (the shards of a
+  // multi-GPU MSM: one more front end costs less than three quarters of the copy).
+  unsigned chunks = ctx->msm_host_chunks > 0 ? (unsigned)ctx->msm_host_chunks
+                                             : (n >= ((size_t)1 << 23) ? 3u : (n >= ((size_t)1 << 20) ? 2u : 1u));
   if (chunks > 8) chunks = 8;
   if (n < 4096 * (size_t)chunks) chunks = 1;
   if (chunks == 1) {
@@ -341,8 +343,10 @@ static int msm_host_scalars(b200zk_ctx* ctx, const b200zk_bases* bases, size_t f
     return msm_run(ctx, bases, first_base, sc, n, stage, out_kind);
   }
   size_t bound[9];
-  if (ctx->msm_host_chunks == 0) {
+  if (ctx->msm_host_chunks == 0 && chunks == 3) {
     bound[0] = 0; bound[1] = n / 8; bound[2] = n / 2; bound[3] = n;
+  } else if (ctx->msm_host_chunks == 0) {
+    bound[0] = 0; bound[1] = n / 4; bound[2] = n;
   } else {
     const size_t per = (n + chunks - 1) / chunks;
     for (unsigned i = 0; i <= chunks; i++) bound[i] = (size_t)i * per < n ? (size_t)i * per : n;
