@@ -1385,7 +1385,8 @@ static int prove_impl(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solution
 
   // P14: opening of Z at w*zeta
   B200ZK_TRY(divide_x_minus_a(ctx, pk, pk->bz, n + 3, zeta_shift, pk->quot));
-  B200ZK_TRY(commit_fork(ctx, pk, pk->quot, n + 2, 15));  // ZShiftedOpening.H, on its own lane until the fetch below
+  B200ZK_TRY(commit_fork(ctx, pk, pk->quot, n + 2, 15));  // ZShiftedOpening.H, on its own lane until the very end: the
+                                                          // batched opening below neither needs it nor rewrites pk->quot
 
   // P15: linearised polynomial
   {
@@ -1427,10 +1428,7 @@ static int prove_impl(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solution
                     pts + 64 * 10);
   }
   tr.mark("zs_div_lin_fold_evals");
-  B200ZK_TRY(commit_join(ctx));  // the lane of ZShiftedOpening.H (pk->quot is rewritten below)
-  tr.mark("zs_commit_join");
   B200ZK_TRY(fetch_scalars(ctx, pk, 6, 2, sc + 6));
-  B200ZK_TRY(fetch_points(ctx, pk, 15, 1, pts + 64 * 8));  // pts[8] = ZShiftedOpening.H
   const Fe4 claimed[7] = {sc[6], sc[7], lz, rz, oz, s1z, s2z};
   Transcript kz;
   kz.begin("gamma");
@@ -1457,10 +1455,15 @@ static int prove_impl(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solution
     k_fold7<<<nblocks(n + 3, 256), 256, 0, st>>>(f);
     B200ZK_LAUNCH_CHECK(ctx, "k_fold7");
   }
-  B200ZK_TRY(divide_x_minus_a(ctx, pk, pk->folded, n + 3, zeta, pk->quot));
+  // the quotient goes to pk->lin (dead once k_fold7 has read it): pk->quot still feeds the MSM on the other lane, and the
+  // two opening commitments are in flight together
+  B200ZK_TRY(divide_x_minus_a(ctx, pk, pk->folded, n + 3, zeta, pk->lin));
   tr.mark("fold_div");
-  B200ZK_TRY(commit(ctx, pk, pk->quot, n + 2, 2));  // slot 2: BatchedProof.H
+  B200ZK_TRY(commit(ctx, pk, pk->lin, n + 2, 2));  // slot 2: BatchedProof.H
   tr.mark("batched_commit");
+  B200ZK_TRY(commit_join(ctx));  // the lane of ZShiftedOpening.H
+  tr.mark("zs_commit_join");
+  B200ZK_TRY(fetch_points(ctx, pk, 15, 1, pts + 64 * 8));  // pts[8] = ZShiftedOpening.H
   uint32_t dist_err = 0;
   if (dist) B200ZK_CUDA(ctx, cudaMemcpyAsync(&dist_err, pk->dist_err, 4, cudaMemcpyDeviceToHost, st));
   B200ZK_TRY(fetch_points(ctx, pk, 2, 1, pts + 64 * 7));
