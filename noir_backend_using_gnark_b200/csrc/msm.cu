@@ -36,7 +36,7 @@ static constexpr size_t TINY_MAX_TERMS = (size_t)1 << 17;
 static constexpr unsigned SMALL_TABLE_W = 43;     // 6-bit windows
 static constexpr size_t SMALL_TABLE_N = 2048;     // head of a large base set that also gets the narrow-window table  // (points x windows) up to which the bucket pipeline is skipped
 static constexpr int MAX_WINDOWS = 64;
-static constexpr int SLICE = 1024;             // chunk results per CTA in the bit-plane sums
+static constexpr int SLICE = 4096;             // chunk results per CTA in the bit-plane sums (a power of two)
 static constexpr int MAX_PLANES = 24;
 static constexpr unsigned NO_KEY = 0x7fffffffu;                   // record of a zero digit in the scatter passes' key stream
 // scatter passes: a pass should leave no more partially written 32-byte sectors open (one per bucket) than L2 keeps until
@@ -558,7 +558,10 @@ __global__ void __launch_bounds__(128) msm_reduce_r1_kernel(const void* __restri
   g1_store_xyzz(acc_out, t, a);
 }
 
-// grid = (slices, planes, sets)
+// grid = (slices, planes, sets).  A thread visits only the chunk results that belong to its plane (those with bit
+// plane-1 of the chunk index set), enumerated directly — no lane idles through the other half — and a CTA covers 4096
+// chunk results, so the shared-memory tree (12 warp-wide additions with mostly idle lanes) is paid once per 8-16
+// additions of every thread instead of once per 4.
 __global__ void __launch_bounds__(BIG_THREADS) msm_reduce_r2_kernel(const void* __restrict__ run, const void* __restrict__ acc_in,
                                                                     unsigned chunks_per_set, unsigned nslices,
                                                                     void* __restrict__ partial) {
@@ -566,23 +569,34 @@ __global__ void __launch_bounds__(BIG_THREADS) msm_reduce_r2_kernel(const void* 
   G1XYZZ* sh_pts = reinterpret_cast<G1XYZZ*>(big_smem);
   const unsigned slice = blockIdx.x, plane = blockIdx.y, set = blockIdx.z;
   const unsigned lo = slice * SLICE;
-  const unsigned hi = lo + SLICE < chunks_per_set ? lo + SLICE : chunks_per_set;
-  G1XYZZ acc = g1_xyzz_inf();
-  for (unsigned t = lo + threadIdx.x; t < hi; t += BIG_THREADS) {
-    const size_t idx = (size_t)set * chunks_per_set + t;
-    if (plane == 0) {
-      G1XYZZ q = g1_load_xyzz(acc_in, idx);
-      g1_add(acc, q);
-    } else if ((t >> (plane - 1)) & 1u) {
-      G1XYZZ q = g1_load_xyzz(run, idx);
-      g1_add(acc, q);
+  const unsigned hi = lo + SLICE < chunks_per_set ? lo + SLICE : chunks_per_set;   // hi - lo is a power of two
+  const unsigned len = hi - lo;
+  // members of this plane inside [lo, hi): all of them (plane 0, or a bit above the slice that is set), none (such a bit
+  // clear), or every second group of 2^b
+  unsigned cnt = len, b = 0;
+  bool spread = false;
+  if (plane) {
+    b = plane - 1;
+    if ((1u << b) >= len) cnt = ((lo >> b) & 1u) ? len : 0u;
+    else {
+      cnt = len >> 1;
+      spread = true;
     }
+  }
+  G1XYZZ acc = g1_xyzz_inf();
+  const void* src = plane ? run : acc_in;
+  for (unsigned i = threadIdx.x; i < cnt; i += BIG_THREADS) {
+    const unsigned t = lo + (spread ? (((i >> b) << (b + 1)) | (1u << b) | (i & ((1u << b) - 1u))) : i);
+    G1XYZZ q = g1_load_xyzz(src, (size_t)set * chunks_per_set + t);
+    g1_add(acc, q);
   }
   block_reduce_xyzz(acc, sh_pts);
   if (threadIdx.x == 0) g1_store_xyzz(partial, ((size_t)set * gridDim.y + plane) * nslices + slice, acc);
 }
 
-// grid = sets, block = 8 warps; warp w finishes planes w, w+8, ...
+// grid = sets, block = 8 warps; warp w finishes planes w, w+8, ...; then warp 0 weighs the planes — lane k doubles plane
+// k up to its weight 2^(k-1+chunk_log) (all lanes step together, 2.6 us per doubling) and a shuffle tree adds them: about
+// 20 dependent doublings + 5 additions instead of a Horner chain of one doubling AND one addition per plane on one thread
 __global__ void __launch_bounds__(256) msm_reduce_r3_kernel(const void* __restrict__ partial, unsigned nplanes,
                                                             unsigned nslices, unsigned chunk_log, void* __restrict__ set_sums) {
   __shared__ G1XYZZ plane_sum[MAX_PLANES];
@@ -597,15 +611,17 @@ __global__ void __launch_bounds__(256) msm_reduce_r3_kernel(const void* __restri
     if (lane == 0) plane_sum[plane] = acc;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    G1XYZZ s = g1_xyzz_inf();
-    for (int k = (int)nplanes - 1; k >= 1; k--) {  // sum_k 2^(k-1) P_k
-      g1_double(s);
-      g1_add(s, plane_sum[k]);
+  if (warp == 0) {
+    G1XYZZ v = lane < nplanes ? plane_sum[lane] : g1_xyzz_inf();
+    const unsigned mine = (lane == 0 || lane >= nplanes) ? 0u : lane - 1 + chunk_log;   // S = P_0 + 2^chunk_log sum_k 2^(k-1) P_k
+    const unsigned most = nplanes >= 2 ? nplanes - 2 + chunk_log : 0u;
+    for (unsigned j = 0; j < most; j++) {
+      G1XYZZ d = v;
+      g1_double(d);
+      if (j < mine) v = d;
     }
-    for (unsigned k = 0; k < chunk_log; k++) g1_double(s);
-    g1_add(s, plane_sum[0]);
-    g1_store_xyzz(set_sums, set, s);
+    v = warp_sum_xyzz(v);
+    if (lane == 0) g1_store_xyzz(set_sums, set, v);
   }
 }
 
