@@ -289,6 +289,17 @@ inline G2 g2_mul(const G2& p, const Fe4& k_mont) {
   }
   return acc;
 }
+// membership in the order-r subgroup of the twist (its cofactor is not 1): [r]Q = infinity.  gnark's G2 decoder performs
+// this check on every decoded point; here it guards the two G2 elements read from srs.hex (two 254-bit ladders, < 1 ms).
+inline bool g2_in_subgroup(const G2& q) {
+  if (q.inf) return true;
+  G2 acc; acc.x = acc.y = f2_zero(); acc.inf = true;
+  for (int b = 255; b >= 0; b--) {
+    acc = g2_add(acc, acc);
+    if ((HFR.m[b / 64] >> (b % 64)) & 1) acc = g2_add(acc, q);
+  }
+  return acc.inf;
+}
 // G2Affine.Bytes(): X.A1 || X.A0 (32-byte BE each), flags in the first byte; y sign: A1 decides unless it is zero
 inline bool f2_lex_largest(const Fp2& y) { return host::is_zero(y.a1) ? fp_lex_largest(y.a0) : fp_lex_largest(y.a1); }
 inline void g2_compress(const G2& p, uint8_t out[64]) {

@@ -165,6 +165,7 @@ bool try_load_srs(State& s) {  // LoadSRS (common.go:86-105); the G1 part goes t
   size_t n = ((size_t)raw[0] << 24) | ((size_t)raw[1] << 16) | ((size_t)raw[2] << 8) | raw[3];
   if (raw.size() != 4 + 32 * n + 128 || n == 0) return false;
   if (!g2_decompress(raw.data() + 4 + 32 * n, &s.g2[0]) || !g2_decompress(raw.data() + 4 + 32 * n + 64, &s.g2[1])) return false;
+  if (!g2_in_subgroup(s.g2[0]) || !g2_in_subgroup(s.g2[1])) return false;   // as gnark's decoder: points of the twist outside G2 are refused
   raw.resize(4 + 32 * n);
   s.srs_file = std::move(raw);
   s.srs_n = n;

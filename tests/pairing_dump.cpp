@@ -44,5 +44,22 @@ int main(int argc, char** argv) {
     return 1;
   }
   printf("%d %d %.2f\n", ok ? 1 : 0, bad ? 1 : 0, std::chrono::duration<double, std::milli>(t1 - t0).count());
+  // subgroup membership (what guards the G2 elements of srs.hex): b*G2 is in the order-r subgroup; the first point of
+  // the twist with x = (k, 0), k = 1, 2, ... is not (the twist's cofactor is ~2^254)
+  G2 off;
+  off.inf = true;
+  unsigned k = 0;
+  while (off.inf) {
+    Fp2 x;
+    x.a0 = fp_small(++k);
+    x.a1 = fp_zero();
+    Fp2 y;
+    if (f2_sqrt(f2_add(f2_mul(f2_mul(x, x), x), twist_b()), &y)) {
+      off.x = x;
+      off.y = y;
+      off.inf = false;
+    }
+  }
+  printf("%d %d %u\n", g2_in_subgroup(q) ? 1 : 0, g2_in_subgroup(off) ? 1 : 0, k);
   return 0;
 }

@@ -30,6 +30,8 @@ def test_pairing_value_matches_the_oracle(dumper, a, b):
     ok, bad, ms = out[2].split()
     assert (ok, bad) == ("1", "0")                      # e(aG, bH) e(-abG, H) == 1, and != 1 for ab + 1
     assert float(ms) < 500
+    in_g2, off_g2, _k = out[3].split()
+    assert (in_g2, off_g2) == ("1", "0")                # [r]Q = O for Q in G2, not for a point of the twist outside it
 
 
 def test_hard_part_expansion_is_exact():
