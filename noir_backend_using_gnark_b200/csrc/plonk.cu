@@ -183,7 +183,7 @@ __global__ void k_z_terms(const uint4* __restrict__ l, const uint4* __restrict__
 }
 
 // ratio[i] = num[i] / den[i] with one inversion per chunk (Montgomery's trick); result overwrites num, den is scratch
-static constexpr int INV_CHUNK = 32;
+static constexpr int INV_CHUNK = 128;   // one Fermat inversion (267 multiplications) per chunk: 32 rows cost 8.3 of them per row
 __global__ void __launch_bounds__(128) k_batch_ratio(uint4* num, uint4* den, uint4* scratch, size_t n) {
   size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   size_t lo = t * INV_CHUNK;
