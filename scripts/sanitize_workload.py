@@ -64,6 +64,14 @@ if "msm" in parts:
         assert zk.MultiExp(srs, sc) == r0
         lib.b200zk_msm_set_window(ctx.handle, 0)
     lib.b200zk_msm_set_pair_rounds(ctx.handle, -1)
+    for passes in (2, 9):                          # scatter in bucket-range passes over the parked key records
+        lib.b200zk_msm_set_scatter_passes(ctx.handle, passes)
+        assert zk.MultiExp(srs, sc) == r0
+        assert zk.MultiExp(srs, same) == r1
+        lib.b200zk_msm_set_window(ctx.handle, 9)
+        assert zk.MultiExp(srs, sc) == r0
+        lib.b200zk_msm_set_window(ctx.handle, 0)
+    lib.b200zk_msm_set_scatter_passes(ctx.handle, 0)
     lib.b200zk_msm_set_small_path(ctx.handle, 1)
     comp = srs.download_compressed(0, 64)
     zk.SRS.FromCompressed(comp, ctx).close()
