@@ -8,11 +8,15 @@
 //                once; every (point, window) pair then lands in ONE shared set of 2^(c-1) buckets, which removes the
 //                per-window reduction and the Horner tail and lets c grow to ~log2(n)-2 (fewer additions per point)
 // Pipeline (all on the context stream, no host synchronisation):
-//   1 msm_hist_kernel        scalar: Montgomery -> regular, signed digits, bucket histogram (global atomics)
+//   1 msm_hist_kernel        scalar: Montgomery -> regular, signed digits, bucket histogram (global atomics); for large
+//                            sorts it also parks a (bucket | sign) record per (point, window) pair
 //   2 exclusive scan          bucket start offsets (CUB)
-//   3 msm_scatter_kernel     counting sort: (table index | sign) grouped by bucket (two alternatives were built and
-//                            measured no better — a two-level partition + shared-memory scatter, and a CUB radix sort of
-//                            (bucket, entry) records: profiles/r02_msm_frontend.md)
+//   3 msm_scatter_kernel     counting sort: (table index | sign) grouped by bucket; with more than 2^19 buckets as
+//     msm_scatter_pass_kernel bucket-range passes over the parked records, so that the partially written sectors of a
+//                            pass stay in L2 (the single pass is bound by DRAM read-modify-writes of its random 4-byte
+//                            stores, not by its atomics).  Two other front ends were built and measured no better — a
+//                            two-level partition + shared-memory scatter, a CUB radix sort: profiles/r02_msm_frontend.md
+//   4a msm_pair_kernel       optional batched-affine pre-summation of the runs (off: slower on this part)
 //   4 msm_accumulate_kernel  one thread per bucket walks its run: 64-byte affine gathers (next point prefetched),
 //                            extended-Jacobian mixed additions; over-long runs (skewed scalars) are left to
 //   4b msm_big_* kernels     which split a run over many CTAs and tree-reduce the partial sums in shared memory
@@ -127,9 +131,9 @@ __global__ void __launch_bounds__(256) msm_hist_kernel(const uint4* __restrict__
   });
 }
 
-// Every thread first issues ALL of its point's returning atomics (one per window, positions kept in registers) and
-// only then the dependent stores: W atomics in flight per thread instead of one (the kernel is bound by the latency
-// of the returning atomic, not by its throughput: ncu long_scoreboard 200 cycles per issue at 88 % occupancy).
+// Single-pass scatter (bucket sets of up to 2^19 buckets, small sorts): every thread first issues ALL of its point's
+// returning atomics (one per window, positions kept in registers) and only then the dependent stores — W atomics in
+// flight per thread instead of one.
 template <int MAXW>
 __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint4* __restrict__ scalars, size_t n, MsmShape sh,
                                                           unsigned* __restrict__ cursor, unsigned* __restrict__ sorted) {
