@@ -161,22 +161,30 @@ __global__ void k_blind(uint4* p, size_t n, const uint4* __restrict__ blinding, 
 }
 
 // numerator / denominator of the copy-constraint ratio at row j
+// (beta * u^k comes from the host for k = 0, 1, 2: beta * u^k * w^j is then ONE product per term instead of up to three)
+struct BetaShift {
+  FrArg bu[3];
+};
 __global__ void k_z_terms(const uint4* __restrict__ l, const uint4* __restrict__ r, const uint4* __restrict__ o,
-                          const int64_t* __restrict__ perm, const uint4* __restrict__ tw, unsigned log2n, FrArg beta_a,
+                          const int64_t* __restrict__ perm, const uint4* __restrict__ tw, unsigned log2n, BetaShift bs,
                           FrArg gamma_a, uint4* num, uint4* den) {
   const size_t n = (size_t)1 << log2n;
   size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (j >= n) return;
-  const Fr beta = arg(beta_a), gamma = arg(gamma_a);
+  const Fr gamma = arg(gamma_a);
+  const Fr wj = omega_pow(tw, j, n >> 1);
   Fr w[3] = {fe_load<FrParams>(l + 2 * j), fe_load<FrParams>(r + 2 * j), fe_load<FrParams>(o + 2 * j)};
-  Fr a = fe_one<FrParams>(), b = fe_one<FrParams>();
+  Fr a, b;
 #pragma unroll
   for (int k = 0; k < 3; k++) {
-    Fr wg = fe_add(w[k], gamma);
-    Fr id = ident_value(tw, (uint64_t)k * n + j, log2n);
-    Fr sg = ident_value(tw, (uint64_t)perm[(size_t)k * n + j], log2n);
-    a = fe_mul(a, fe_add(wg, fe_mul(beta, id)));
-    b = fe_mul(b, fe_add(wg, fe_mul(beta, sg)));
+    const Fr wg = fe_add(w[k], gamma);
+    const uint64_t sp = (uint64_t)perm[(size_t)k * n + j];          // sigma: position in [0, 3n)
+    const unsigned sk = (unsigned)(sp >> log2n);
+    const Fr bsk = arg(sk == 0 ? bs.bu[0] : (sk == 1 ? bs.bu[1] : bs.bu[2]));
+    const Fr ta = fe_add(wg, fe_mul(arg(bs.bu[k]), wj));                                  // w + gamma + beta * u^k * w^j
+    const Fr tb = fe_add(wg, fe_mul(bsk, omega_pow(tw, sp & (n - 1), n >> 1)));           // w + gamma + beta * sigma
+    a = k == 0 ? ta : fe_mul(a, ta);
+    b = k == 0 ? tb : fe_mul(b, tb);
   }
   fe_store(num + 2 * j, a);
   fe_store(den + 2 * j, b);
@@ -1206,7 +1214,15 @@ static int prove_impl(b200zk_ctx* ctx, b200zk_plonk_pk* pk, const void* solution
   const uint4* tw_n = (const uint4*)ctx->domains[log2n].tw_fwd;
   uint4* num = pk->lin;       // scratch: lin / folded / quot are free until P15
   uint4* den = pk->folded;
-  k_z_terms<<<nblocks(n, 128), 128, 0, st>>>(pk->l, pk->r, pk->o, pk->perm, tw_n, log2n, to_arg(beta), to_arg(gamma), num, den);
+  BetaShift bshift;
+  {
+    const Fe4 u5 = host::from_u64(HFR, 5);
+    const Fe4 b1 = host::mul(HFR, beta, u5);
+    bshift.bu[0] = to_arg(beta);
+    bshift.bu[1] = to_arg(b1);
+    bshift.bu[2] = to_arg(host::mul(HFR, b1, u5));
+  }
+  k_z_terms<<<nblocks(n, 128), 128, 0, st>>>(pk->l, pk->r, pk->o, pk->perm, tw_n, log2n, bshift, to_arg(gamma), num, den);
   B200ZK_LAUNCH_CHECK(ctx, "k_z_terms");
   k_batch_ratio<<<nblocks((n + INV_CHUNK - 1) / INV_CHUNK, 128), 128, 0, st>>>(num, den, pk->quot, n);
   B200ZK_LAUNCH_CHECK(ctx, "k_batch_ratio");
